@@ -1,0 +1,477 @@
+// C ABI of libresep_b200.so (include/resep_b200.h): handle lifetime, weight upload, per-shape
+// plans, workspace carving and the forward-pass orchestration that restates
+// SepformerSeparation.separate_batch (speechbrain/inference/separation.py), called by the
+// reference at /root/reference/back/api.py:1077.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "resep_internal.cuh"
+#include "resep_tc.cuh"
+
+namespace resep {
+
+static thread_local std::string g_create_err;
+
+int set_err(ResepHandle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------ weights
+struct ArenaBuilder {
+  std::vector<unsigned char> host;
+  size_t add(const void* src, size_t bytes) {
+    size_t off = align_up(host.size(), 256);
+    host.resize(off + bytes);
+    std::memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+  size_t add_f32(const float* src, size_t n) { return add(src, n * sizeof(float)); }
+  size_t add_bf16(const float* src, size_t n) {
+    std::vector<bf16> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
+    return add(tmp.data(), n * sizeof(bf16));
+  }
+};
+
+static int upload_weights(ResepHandle* h, const ResepWeights* w) {
+  if (!w || !w->enc_w || !w->dec_w || !w->prelu_a || !w->fc_w || !w->fc_b || !w->pe)
+    return set_err(h, RESEP_EINVAL, "null weight pointer");
+  if (w->pe_rows < CHUNK) return set_err(h, RESEP_EINVAL, "pe_rows must be >= 150");
+  ArenaBuilder ab;
+  struct Fix { const void** slot; size_t off; };
+  std::vector<Fix> fixes;
+  WeightsDev& d = h->w;
+  auto F = [&](const float*& slot, const float* src, size_t n) {
+    fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_f32(src, n)});
+  };
+  auto Bf = [&](const bf16*& slot, const float* src, size_t n) {
+    fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_bf16(src, n)});
+  };
+  F(d.enc_w, w->enc_w, D * KSZ);
+  F(d.dec_w, w->dec_w, D * KSZ);
+  F(d.prelu_a, w->prelu_a, 1);
+  F(d.fc_w, w->fc_w, NSPK * D * D);
+  F(d.fc_b, w->fc_b, NSPK * D);
+  F(d.pe, w->pe, (size_t)w->pe_rows * D);
+  Bf(d.fc_w_bf, w->fc_w, NSPK * D * D);
+  d.pe_rows = w->pe_rows;
+  const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
+  for (int b = 0; b < 3; ++b) {
+    const ResepBlockWeights& sb = *src_blocks[b];
+    BlockDev& db = d.blk[b];
+    if (!sb.final_norm_w || !sb.final_norm_b || !sb.gln_w || !sb.gln_b) return set_err(h, RESEP_EINVAL, "null block weight");
+    F(db.fn_w, sb.final_norm_w, D); F(db.fn_b, sb.final_norm_b, D);
+    F(db.gln_w, sb.gln_w, D); F(db.gln_b, sb.gln_b, D);
+    for (int l = 0; l < NL; ++l) {
+      const ResepLayerWeights& s = sb.layers[l];
+      LayerDev& t = db.layers[l];
+      if (!s.norm1_w || !s.norm1_b || !s.in_proj_w || !s.in_proj_b || !s.out_proj_w || !s.out_proj_b || !s.norm2_w ||
+          !s.norm2_b || !s.ffn1_w || !s.ffn1_b || !s.ffn2_w || !s.ffn2_b)
+        return set_err(h, RESEP_EINVAL, "null layer weight");
+      F(t.norm1_w, s.norm1_w, D); F(t.norm1_b, s.norm1_b, D);
+      F(t.in_w, s.in_proj_w, 3 * D * D); F(t.in_b, s.in_proj_b, 3 * D);
+      F(t.out_w, s.out_proj_w, D * D); F(t.out_b, s.out_proj_b, D);
+      F(t.norm2_w, s.norm2_w, D); F(t.norm2_b, s.norm2_b, D);
+      F(t.f1_w, s.ffn1_w, (size_t)FFN * D); F(t.f1_b, s.ffn1_b, FFN);
+      F(t.f2_w, s.ffn2_w, (size_t)D * FFN); F(t.f2_b, s.ffn2_b, D);
+      Bf(t.in_w_bf, s.in_proj_w, 3 * D * D);
+      Bf(t.out_w_bf, s.out_proj_w, D * D);
+      Bf(t.f1_w_bf, s.ffn1_w, (size_t)FFN * D);
+      Bf(t.f2_w_bf, s.ffn2_w, (size_t)D * FFN);
+    }
+  }
+  if (h->arena == nullptr || h->arena_bytes < ab.host.size()) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
+    RESEP_CUDA(h, cudaMalloc(&h->arena, ab.host.size()));
+    h->arena_bytes = ab.host.size();
+  }
+  RESEP_CUDA(h, cudaMemcpy(h->arena, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
+  for (auto& f : fixes) *f.slot = static_cast<unsigned char*>(h->arena) + f.off;
+  return RESEP_OK;
+}
+
+// ------------------------------------------------------------------------------ plans
+static void free_plan(Plan* p) {
+  if (!p) return;
+  if (p->dev) cudaFree(p->dev);
+  delete p;
+}
+
+static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_t* item_len, int batch_mode,
+                    cudaStream_t st, Plan** out) {
+  std::vector<int64_t> key;
+  key.reserve(2 + 2 * (size_t)B);
+  key.push_back(B);
+  key.push_back(batch_mode);
+  for (int i = 0; i < B; ++i) { key.push_back(item_off[i]); key.push_back(item_len[i]); }
+  h->tick++;
+  for (Plan* p : h->plans)
+    if (p->key == key) { p->last_use = h->tick; *out = p; return RESEP_OK; }
+
+  Plan* p = new (std::nothrow) Plan();
+  if (!p) return set_err(h, RESEP_EINVAL, "out of host memory");
+  p->key = key;
+  p->B = B;
+  std::vector<int> item_L(B), item_row0(B), item_S(B);
+  int64_t chunks = 0;
+  for (int i = 0; i < B; ++i) {
+    const int64_t T = item_len[i];
+    if (T < KSZ) {
+      delete p;
+      return set_err(h, RESEP_ESHORT, "item " + std::to_string(i) + " has " + std::to_string(T) +
+                                          " samples; kernel size (16) can't be greater than actual input size");
+    }
+    const int64_t L = (T - KSZ) / STRIDE + 1;
+    if (L > 2000000000LL / D) { delete p; return set_err(h, RESEP_EINVAL, "item too long"); }
+    item_L[i] = (int)L;
+    item_S[i] = (int)(L / CHUNK + 1);   // rest = K - L % K is in [1, K]: a full zero chunk when L % K == 0
+    item_row0[i] = (int)(chunks * CHUNK);
+    chunks += item_S[i];
+    if (chunks * CHUNK > 2000000000LL) { delete p; return set_err(h, RESEP_EINVAL, "batch too large (token rows overflow int32)"); }
+  }
+  p->n_chunks = chunks;
+  p->M = chunks * CHUNK;
+  std::vector<int> chunk_item(chunks), chunk_frame0(chunks), mem_pos(chunks);
+  std::vector<int> mem_seq_off;
+  {
+    int64_t c = 0;
+    for (int i = 0; i < B; ++i)
+      for (int s = 0; s < item_S[i]; ++s, ++c) { chunk_item[c] = i; chunk_frame0[c] = s * CHUNK; }
+  }
+  if (batch_mode == RESEP_BATCH_COUPLED) {
+    mem_seq_off = {0, (int)chunks};
+  } else {
+    mem_seq_off.push_back(0);
+    for (int i = 0; i < B; ++i) mem_seq_off.push_back(mem_seq_off.back() + item_S[i]);
+  }
+  p->n_mem_seq = (int)mem_seq_off.size() - 1;
+  std::vector<int> mem_tile_seq, mem_tile_q0;
+  for (int s = 0; s < p->n_mem_seq; ++s) {
+    const int len = mem_seq_off[s + 1] - mem_seq_off[s];
+    p->max_mem_len = std::max(p->max_mem_len, len);
+    for (int j = 0; j < len; ++j) mem_pos[mem_seq_off[s] + j] = j;
+    for (int q0 = 0; q0 < len; q0 += 128) { mem_tile_seq.push_back(s); mem_tile_q0.push_back(q0); }
+  }
+  p->n_mem_tiles = (int)mem_tile_seq.size();
+  if (p->max_mem_len > h->w.pe_rows) {
+    delete p;
+    return set_err(h, RESEP_EPOS, "memory sequence of " + std::to_string(p->max_mem_len) +
+                                      " chunks exceeds the positional-encoding table");
+  }
+  std::vector<int> dec_tile_item, dec_tile_slot0;
+  for (int i = 0; i < B; ++i) {
+    const int64_t slots = (item_len[i] + STRIDE - 1) / STRIDE;
+    for (int64_t q = 0; q < slots; q += 32) { dec_tile_item.push_back(i); dec_tile_slot0.push_back((int)q); }
+  }
+  p->n_dec_tiles = (int)dec_tile_item.size();
+
+  // pack every table into one host blob -> one device allocation, one copy
+  std::vector<unsigned char> blob;
+  auto put = [&](const void* src, size_t bytes) {
+    size_t off = align_up(blob.size(), 16);
+    blob.resize(off + bytes);
+    if (bytes) std::memcpy(blob.data() + off, src, bytes);
+    return off;
+  };
+  const size_t o_off = put(item_off, sizeof(int64_t) * B), o_len = put(item_len, sizeof(int64_t) * B);
+  const size_t o_L = put(item_L.data(), sizeof(int) * B), o_row0 = put(item_row0.data(), sizeof(int) * B);
+  const size_t o_ci = put(chunk_item.data(), sizeof(int) * chunks), o_cf = put(chunk_frame0.data(), sizeof(int) * chunks);
+  const size_t o_mp = put(mem_pos.data(), sizeof(int) * chunks);
+  const size_t o_ms = put(mem_seq_off.data(), sizeof(int) * mem_seq_off.size());
+  const size_t o_mts = put(mem_tile_seq.data(), sizeof(int) * mem_tile_seq.size());
+  const size_t o_mtq = put(mem_tile_q0.data(), sizeof(int) * mem_tile_q0.size());
+  const size_t o_dti = put(dec_tile_item.data(), sizeof(int) * dec_tile_item.size());
+  const size_t o_dts = put(dec_tile_slot0.data(), sizeof(int) * dec_tile_slot0.size());
+  p->dev_bytes = blob.size();
+  cudaError_t e = cudaMalloc(&p->dev, p->dev_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->dev, blob.data(), blob.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // blob is a stack-lifetime pageable buffer
+  if (e != cudaSuccess) {
+    free_plan(p);
+    return set_err(h, RESEP_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+  }
+  unsigned char* base = static_cast<unsigned char*>(p->dev);
+  p->d_item_off = reinterpret_cast<const int64_t*>(base + o_off);
+  p->d_item_len = reinterpret_cast<const int64_t*>(base + o_len);
+  p->d_item_L = reinterpret_cast<const int*>(base + o_L);
+  p->d_item_row0 = reinterpret_cast<const int*>(base + o_row0);
+  p->d_chunk_item = reinterpret_cast<const int*>(base + o_ci);
+  p->d_chunk_frame0 = reinterpret_cast<const int*>(base + o_cf);
+  p->d_mem_pos = reinterpret_cast<const int*>(base + o_mp);
+  p->d_mem_seq_off = reinterpret_cast<const int*>(base + o_ms);
+  p->d_mem_tile_seq = reinterpret_cast<const int*>(base + o_mts);
+  p->d_mem_tile_q0 = reinterpret_cast<const int*>(base + o_mtq);
+  p->d_dec_tile_item = reinterpret_cast<const int*>(base + o_dti);
+  p->d_dec_tile_slot0 = reinterpret_cast<const int*>(base + o_dts);
+  p->last_use = h->tick;
+  if (h->plans.size() >= 16) {   // evict the least recently used plan (stream-ordered free is safe: cudaFree syncs)
+    auto it = std::min_element(h->plans.begin(), h->plans.end(),
+                               [](const Plan* a, const Plan* b) { return a->last_use < b->last_use; });
+    free_plan(*it);
+    h->plans.erase(it);
+  }
+  h->plans.push_back(p);
+  *out = p;
+  return RESEP_OK;
+}
+
+// ------------------------------------------------------------------------------ workspace
+struct Workspace {
+  float *x0, *a, *o, *y, *qkv, *ctx, *hid, *hc_in, *hc_out;
+  size_t bytes;
+};
+
+static Workspace carve(void* base, int64_t M, int64_t n_chunks) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(static_cast<unsigned char*>(base) + off) : nullptr;
+    off = align_up(off + floats * sizeof(float), 1024);
+    return p;
+  };
+  const size_t rows = (size_t)align_up((size_t)M, 128);   // GEMM tiles may touch a rounded-up row count
+  w.x0 = take(rows * D);
+  w.a = take(rows * D);
+  w.o = take(rows * D);
+  w.y = take(rows * D);
+  w.qkv = take(rows * 3 * D);
+  w.ctx = take(rows * D);
+  w.hid = take(rows * FFN);
+  w.hc_in = take(align_up((size_t)n_chunks, 128) * D);
+  w.hc_out = take(align_up((size_t)n_chunks, 128) * D);
+  w.bytes = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------ forward
+struct SeqDesc {          // the sequences one transformer block runs over
+  int64_t rows;
+  int n_seq;
+  int seq_len;            // equal-length case (seq_off == nullptr)
+  const int* seq_off;     // ragged case
+  const int* pos;         // position of each row in its sequence (nullptr: row % seq_len)
+  const int* tile_seq;    // attention query tiles of the ragged case
+  const int* tile_q0;
+  int n_tiles;
+};
+
+static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc& sd, const Workspace& ws, int precision,
+                     cudaStream_t st) {
+  int rc;
+  if (precision == RESEP_PREC_FP32) {
+    if ((rc = launch_layernorm<float>(h, o, lw.norm1_w, lw.norm1_b, ws.y, sd.rows, st))) return rc;
+    if ((rc = launch_gemm_f32(h, ws.y, lw.in_w, lw.in_b, nullptr, ws.qkv, sd.rows, 3 * D, D, false, st))) return rc;
+    if ((rc = launch_attention_f32(h, ws.qkv, ws.ctx, sd.n_seq, sd.seq_len, sd.seq_off, sd.tile_seq, sd.tile_q0,
+                                   sd.n_tiles, st))) return rc;
+    if ((rc = launch_gemm_f32(h, ws.ctx, lw.out_w, lw.out_b, o, o, sd.rows, D, D, false, st))) return rc;
+    if ((rc = launch_layernorm<float>(h, o, lw.norm2_w, lw.norm2_b, ws.y, sd.rows, st))) return rc;
+    if ((rc = launch_gemm_f32(h, ws.y, lw.f1_w, lw.f1_b, nullptr, ws.hid, sd.rows, FFN, D, true, st))) return rc;
+    if ((rc = launch_gemm_f32(h, ws.hid, lw.f2_w, lw.f2_b, o, o, sd.rows, D, FFN, false, st))) return rc;
+    return RESEP_OK;
+  }
+  return tc_run_layer(h, lw, o, sd.rows, sd.n_seq, sd.seq_len, sd.seq_off, sd.tile_seq, sd.tile_q0, sd.n_tiles, ws.y,
+                      ws.qkv, ws.ctx, ws.hid, precision, st);
+}
+
+static int run_block(ResepHandle* h, int blk, const float* xprev, const float* hc, float* xin, float* o, float* out,
+                     float* seq_mean, const SeqDesc& sd, const Workspace& ws, int precision, cudaStream_t st) {
+  int rc;
+  const BlockDev& bw = h->w.blk[blk];
+  if ((rc = launch_block_prologue(h, xprev, hc, xin, o, sd.rows, sd.pos, sd.seq_len, st))) return rc;
+  for (int l = 0; l < NL; ++l)
+    if ((rc = run_layer(h, bw.layers[l], o, sd, ws, precision, st))) return rc;
+  return launch_block_epilogue(h, o, bw.fn_w, bw.fn_b, bw.gln_w, bw.gln_b, xin, out, seq_mean, sd.n_seq, sd.seq_len,
+                               sd.seq_off, st);
+}
+
+static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
+                        float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
+                        cudaStream_t st, const ResepDebugOut* dbg) {
+  if (!h) return RESEP_EINVAL;
+  if (!mix || !item_off || !item_len || !est || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or B <= 0");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  if (batch_mode != RESEP_BATCH_COUPLED && batch_mode != RESEP_BATCH_INDEPENDENT)
+    return set_err(h, RESEP_EINVAL, "unknown batch_mode");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  Plan* p = nullptr;
+  int rc = get_plan(h, B, item_off, item_len, batch_mode, st, &p);
+  if (rc) return rc;
+  Workspace ws = carve(workspace, p->M, p->n_chunks);
+  if (!workspace || workspace_bytes < ws.bytes)
+    return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
+  if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
+
+  if ((rc = launch_encoder_chunked(h, mix, *p, ws.x0, st))) return rc;
+  if (dbg && dbg->enc) RESEP_CUDA(h, cudaMemcpyAsync(dbg->enc, ws.x0, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  SeqDesc intra{p->M, (int)p->n_chunks, CHUNK, nullptr, nullptr, nullptr, nullptr, 0};
+  SeqDesc mem{p->n_chunks, p->n_mem_seq, 0, p->d_mem_seq_off, p->d_mem_pos, p->d_mem_tile_seq, p->d_mem_tile_q0,
+              p->n_mem_tiles};
+  if (p->n_mem_seq == 1) {   // a single sequence is the equal-length case
+    mem.seq_len = (int)p->n_chunks; mem.seq_off = nullptr; mem.pos = nullptr; mem.tile_seq = nullptr; mem.tile_q0 = nullptr;
+  }
+
+  // seg_model[0](x + 0): skip input is the encoder output itself
+  if ((rc = run_block(h, 0, ws.x0, nullptr, ws.x0, ws.o, ws.a, ws.hc_in, intra, ws, precision, st))) return rc;
+  if (dbg && dbg->seg0) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg0, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (dbg && dbg->chunk_mean)
+    RESEP_CUDA(h, cudaMemcpyAsync(dbg->chunk_mean, ws.hc_in, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // mem_model[0](chunk means): memory transformer over chunk summaries
+  if ((rc = run_block(h, 2, ws.hc_in, nullptr, ws.hc_in, ws.o, ws.hc_out, nullptr, mem, ws, precision, st))) return rc;
+  if (dbg && dbg->mem0)
+    RESEP_CUDA(h, cudaMemcpyAsync(dbg->mem0, ws.hc_out, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // seg_model[1](out + hc)
+  if ((rc = run_block(h, 1, ws.a, ws.hc_out, ws.a, ws.o, ws.a, nullptr, intra, ws, precision, st))) return rc;
+  if (dbg && dbg->seg1) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg1, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  // output_fc (PReLU -> 1x1 conv 128->256) -> ReLU mask -> x encoder features -> decoder
+  float* mask = ws.hid;
+  if (precision == RESEP_PREC_FP32) {
+    if ((rc = launch_prelu(h, ws.a, h->w.prelu_a, ws.y, p->M * D, st))) return rc;
+    if ((rc = launch_gemm_f32(h, ws.y, h->w.fc_w, h->w.fc_b, nullptr, mask, p->M, NSPK * D, D, true, st))) return rc;
+  } else {
+    if ((rc = tc_run_mask(h, ws.a, ws.y, mask, p->M, precision, st))) return rc;
+  }
+  return launch_decoder(h, mask, ws.x0, *p, est, st);
+}
+
+}  // namespace resep
+
+using namespace resep;
+
+extern "C" {
+
+int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, ResepHandle** out) {
+  if (!cfg || !w || !out) return set_err(nullptr, RESEP_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != RESEP_ABI_VERSION) return set_err(nullptr, RESEP_EINVAL, "ABI version mismatch");
+  if (cfg->n_filters != D || cfg->kernel_size != KSZ || cfg->stride != STRIDE || cfg->segment_size != CHUNK ||
+      cfg->n_heads != NH || cfg->d_ffn != FFN || cfg->n_layers != NL || cfg->n_blocks != 2 || cfg->n_spks != NSPK)
+    return set_err(nullptr, RESEP_EINVAL,
+                   "unsupported architecture: kernels are specialised for resepformer-wsj02mix "
+                   "(128 filters, k16 s8, chunk 150, 8 heads, ffn 1024, 8 layers, 2 blocks, 2 speakers)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_err(nullptr, RESEP_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return set_err(nullptr, RESEP_EINVAL, "device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return set_err(nullptr, RESEP_ECUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return set_err(nullptr, RESEP_ENODEVICE, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                                 "; this library holds sm_100a code only");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return set_err(nullptr, RESEP_ECUDA, cudaGetErrorString(e));
+  ResepHandle* h = new (std::nothrow) ResepHandle();
+  if (!h) return set_err(nullptr, RESEP_EINVAL, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  int rc = upload_weights(h, w);
+  if (rc) {
+    g_create_err = h->err;
+    if (h->arena) cudaFree(h->arena);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return RESEP_OK;
+}
+
+int resep_load_weights(ResepHandle* h, const ResepWeights* w) {
+  if (!h) return RESEP_EINVAL;
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  RESEP_CUDA(h, cudaDeviceSynchronize());
+  int rc = upload_weights(h, w);
+  if (rc) return rc;
+  tc_destroy(h);   // packed tensor-core copies are rebuilt lazily from the new weights
+  return RESEP_OK;
+}
+
+int resep_destroy(ResepHandle* h) {
+  if (!h) return RESEP_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  tc_destroy(h);
+  for (Plan* p : h->plans) free_plan(p);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return RESEP_OK;
+}
+
+const char* resep_last_error(const ResepHandle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int64_t resep_launch_count(const ResepHandle* h) { return h ? h->launches : 0; }
+
+int resep_workspace_bytes(ResepHandle* h, int B, const int64_t* item_len, int precision, size_t* bytes) {
+  if (!h) return RESEP_EINVAL;
+  if (!item_len || !bytes || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or B <= 0");
+  (void)precision;
+  int64_t chunks = 0;
+  for (int i = 0; i < B; ++i) {
+    if (item_len[i] < KSZ)
+      return set_err(h, RESEP_ESHORT, "item " + std::to_string(i) + " has " + std::to_string(item_len[i]) +
+                                          " samples; kernel size (16) can't be greater than actual input size");
+    chunks += ((item_len[i] - KSZ) / STRIDE + 1) / CHUNK + 1;
+  }
+  *bytes = carve(nullptr, chunks * CHUNK, chunks).bytes;
+  return RESEP_OK;
+}
+
+int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B, float* est,
+                  void* workspace, size_t workspace_bytes, int precision, int batch_mode, void* stream) {
+  return forward_impl(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode,
+                      static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int resep_forward_debug(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
+                        float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode, void* stream,
+                        const ResepDebugOut* dbg) {
+  return forward_impl(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode,
+                      static_cast<cudaStream_t>(stream), dbg);
+}
+
+int resep_encoder_fwd(ResepHandle* h, const float* mix, int64_t T, float* tokens_out, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!mix || !tokens_out) return set_err(h, RESEP_EINVAL, "null pointer");
+  if (T < KSZ) return set_err(h, RESEP_ESHORT, "kernel size (16) can't be greater than actual input size");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  return launch_encoder_single(h, mix, T, tokens_out, static_cast<cudaStream_t>(stream));
+}
+
+int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, int seq_len, void* workspace,
+                    size_t workspace_bytes, int precision, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!x || block < 0 || block > 2 || layer < 0 || layer >= NL || n_seq <= 0 || seq_len <= 0)
+    return set_err(h, RESEP_EINVAL, "bad argument");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  const int64_t rows = (int64_t)n_seq * seq_len;
+  Workspace ws = carve(workspace, rows, 0);
+  if (!workspace || workspace_bytes < ws.bytes)
+    return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
+  int rc;
+  if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
+  const int blk = block == 2 ? 2 : block;
+  SeqDesc sd{rows, n_seq, seq_len, nullptr, nullptr, nullptr, nullptr, 0};
+  return run_layer(h, h->w.blk[blk].layers[layer], x, sd, ws, precision, static_cast<cudaStream_t>(stream));
+}
+
+int resep_linear_fwd(ResepHandle* h, const float* A, const float* W, const float* bias, float* out, int64_t M, int N,
+                     int K, int relu, int precision, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!A || !W || !bias || !out || M <= 0) return set_err(h, RESEP_EINVAL, "bad argument");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == RESEP_PREC_FP32) return launch_gemm_f32(h, A, W, bias, nullptr, out, M, N, K, relu != 0, st);
+  int rc = tc_init(h);
+  if (rc) return rc;
+  return tc_linear_test(h, A, W, bias, out, M, N, K, relu != 0, precision, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// Internal declarations shared by the translation units of libresep_b200.so.
+// Architecture constants are those of speechbrain/resepformer-wsj02mix.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "resep_b200.h"
+
+namespace resep {
+
+constexpr int D = 128;       // d_model == encoder filters
+constexpr int KSZ = 16;      // encoder / decoder kernel
+constexpr int STRIDE = 8;
+constexpr int CHUNK = 150;   // segment_size K
+constexpr int NH = 8;
+constexpr int DH = 16;
+constexpr int FFN = 1024;
+constexpr int NL = 8;
+constexpr int NSPK = 2;
+constexpr float LN_EPS = 1e-6f;
+constexpr float GLN_EPS = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+
+typedef __nv_bfloat16 bf16;
+
+struct LayerDev {
+  const float *norm1_w, *norm1_b, *in_w, *in_b, *out_w, *out_b, *norm2_w, *norm2_b, *f1_w, *f1_b, *f2_w, *f2_b;
+  const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;
+};
+struct BlockDev {
+  LayerDev layers[NL];
+  const float *fn_w, *fn_b, *gln_w, *gln_b;
+};
+struct WeightsDev {
+  const float *enc_w, *dec_w, *prelu_a, *fc_w, *fc_b, *pe;
+  const bf16* fc_w_bf;
+  int64_t pe_rows;
+  BlockDev blk[3];  // 0 = seg_model[0], 1 = seg_model[1], 2 = mem_model[0]
+};
+
+// Per-call shape tables ("plan"), cached on the handle by shape signature.
+struct Plan {
+  std::vector<int64_t> key;
+  int B = 0;
+  int64_t n_chunks = 0;   // sum_i S_i
+  int64_t M = 0;          // 150 * n_chunks intra tokens
+  int n_mem_seq = 0;      // 1 (coupled) or B (independent)
+  int max_mem_len = 0;
+  int n_mem_tiles = 0;    // attention query tiles over the memory sequences
+  int n_dec_tiles = 0;
+  // one device allocation holding every table below
+  void* dev = nullptr;
+  size_t dev_bytes = 0;
+  const int64_t* d_item_off = nullptr;    // [B] sample offset of item in mix
+  const int64_t* d_item_len = nullptr;    // [B] T
+  const int* d_item_L = nullptr;          // [B] frames
+  const int* d_item_row0 = nullptr;       // [B] first token row of the item (150 * first chunk)
+  const int* d_chunk_item = nullptr;      // [n_chunks]
+  const int* d_chunk_frame0 = nullptr;    // [n_chunks] frame index of the chunk's first row
+  const int* d_mem_pos = nullptr;         // [n_chunks] position of the chunk in its memory sequence
+  const int* d_mem_seq_off = nullptr;     // [n_mem_seq+1]
+  const int* d_mem_tile_seq = nullptr;    // [n_mem_tiles]
+  const int* d_mem_tile_q0 = nullptr;     // [n_mem_tiles]
+  const int* d_dec_tile_item = nullptr;   // [n_dec_tiles]
+  const int* d_dec_tile_slot0 = nullptr;  // [n_dec_tiles]
+  uint64_t last_use = 0;
+};
+
+}  // namespace resep
+
+struct ResepHandle {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  void* arena = nullptr;  // all weights, one allocation
+  size_t arena_bytes = 0;
+  resep::WeightsDev w;
+  std::vector<resep::Plan*> plans;
+  uint64_t tick = 0;
+  int64_t launches = 0;
+  bool tc_ready = false;  // tensor maps for the tcgen05 path built
+  void* tc_state = nullptr;
+};
+
+namespace resep {
+
+// ---------------------------------------------------------------- error plumbing
+int set_err(ResepHandle* h, int code, const std::string& msg);
+#define RESEP_CUDA(h, expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::resep::set_err(h, RESEP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+#define RESEP_LAUNCH_CHECK(h, name)                                                            \
+  do {                                                                                         \
+    (h)->launches++;                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                      \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::resep::set_err(h, RESEP_ECUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---------------------------------------------------------------- fp32 kernels (kernels_simt.cu)
+int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st);
+int launch_encoder_single(ResepHandle* h, const float* mix, int64_t T, float* tokens, cudaStream_t st);
+// o = xin + pe[pos]; if hc != null first xin = xprev + hc[row / rows_per_hc] (written to xin)
+int launch_block_prologue(ResepHandle* h, const float* xprev, const float* hc, float* xin, float* o, int64_t rows,
+                          const int* pos, int seq_len, cudaStream_t st);
+template <typename OutT>
+int launch_layernorm(ResepHandle* h, const float* x, const float* w, const float* b, OutT* y, int64_t rows,
+                     cudaStream_t st);
+// C = A.W^T + bias (relu?) (+ residual, may alias C)
+int launch_gemm_f32(ResepHandle* h, const float* A, const float* W, const float* bias, const float* residual, float* C,
+                    int64_t M, int N, int K, bool relu, cudaStream_t st);
+// generic fp32 attention over sequences; qkv [rows,384] -> ctx [rows,128]
+int launch_attention_f32(ResepHandle* h, const float* qkv, float* ctx, int n_seq, int seq_len, const int* seq_off,
+                         const int* tile_seq, const int* tile_q0, int n_tiles, cudaStream_t st);
+// final LayerNorm + gLN per sequence + skip (+ per-sequence column mean)
+int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const float* fn_b, const float* gln_w,
+                          const float* gln_b, const float* xin, float* out, float* seq_mean, int n_seq, int seq_len,
+                          const int* seq_off, cudaStream_t st);
+int launch_prelu(ResepHandle* h, const float* x, const float* a, float* y, int64_t n, cudaStream_t st);
+template <typename OutT>
+int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st);
+// mask [M,256] (already relu'd), x0 [M,128] -> est
+int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Plan& p, float* est, cudaStream_t st);
+
+// ---------------------------------------------------------------- tensor-core kernels (kernels_tc.cu)
+int tc_init(ResepHandle* h);
+void tc_destroy(ResepHandle* h);
+
+}  // namespace resep

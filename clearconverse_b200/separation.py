@@ -1,0 +1,327 @@
+"""Drop-in for ``speechbrain.inference.separation.SepformerSeparation`` on the one path
+ClearConverse uses it for (/root/reference/back/api.py):
+
+    self.separator = SepformerSeparation.from_hparams(source=..., savedir=..., run_opts={"device": dev})   # :713-717
+    self.separator.load_state_dict(state_dict, strict=False)                                              # :745
+    separated = self.separator.separate_batch(subsegment)        # [1,T] -> [1,T,2]                       # :1077
+
+Same names, argument meaning and error behaviour (Python exceptions; the caller's
+``except Exception`` at api.py:1107 turns them into "[Processing error]" rows).  Behind it a
+PyTorch custom op (CUDA dispatch key only) hands raw device pointers and the current CUDA
+stream to the C ABI of ``libresep_b200.so``.  There is no CPU path: a CPU-only host or a
+missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from collections import namedtuple
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib, weights as _weights
+
+NUM_SPKS = 2
+SAMPLE_RATE = 8000
+KERNEL_SIZE = 16
+
+_IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+
+# ---------------------------------------------------------------------------------------------
+# engine registry: the custom op takes an integer engine id (ops cannot carry Python objects)
+_ENGINES: dict[int, "_Engine"] = {}
+_ENGINES_LOCK = threading.Lock()
+_NEXT_ID = [1]
+
+
+class _Engine:
+    """Owns one ResepHandle (one CUDA device) and a grow-only workspace tensor."""
+
+    def __init__(self, sds: dict, device: torch.device, pe_rows: int):
+        if device.type != "cuda":
+            raise RuntimeError(
+                f"clearconverse_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise RuntimeError("clearconverse_b200: no CUDA device is available; there is no CPU fallback")
+        self.lib = _lib.load_library()
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.packed = _weights.PackedWeights(sds, pe_rows)
+        self.handle = C.c_void_p()
+        cfg = _weights.default_config()
+        rc = self.lib.resep_create(C.byref(cfg), C.byref(self.packed.struct), self.device.index, C.byref(self.handle))
+        _lib.check(self.lib, None, rc)
+        self.workspace = None
+        with _ENGINES_LOCK:
+            self.id = _NEXT_ID[0]
+            _NEXT_ID[0] += 1
+            _ENGINES[self.id] = self
+
+    def reload(self, sds: dict, pe_rows: int):
+        packed = _weights.PackedWeights(sds, pe_rows)
+        _lib.check(self.lib, self.handle, self.lib.resep_load_weights(self.handle, C.byref(packed.struct)))
+        self.packed = packed
+
+    def launch_count(self) -> int:
+        return int(self.lib.resep_launch_count(self.handle))
+
+    def _workspace_for(self, lens: "C.Array", B: int, precision: int) -> torch.Tensor:
+        need = C.c_size_t()
+        _lib.check(self.lib, self.handle, self.lib.resep_workspace_bytes(self.handle, B, lens, precision, C.byref(need)))
+        if self.workspace is None or self.workspace.numel() < need.value:
+            self.workspace = None          # release before growing
+            self.workspace = torch.empty(int(need.value * 1.0) + 1024, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def forward(self, mix_flat: torch.Tensor, offs: list[int], lens: list[int], precision: int, batch_mode: int,
+                debug: dict | None = None) -> torch.Tensor:
+        """mix_flat: 1-D fp32 CUDA tensor holding every item; returns est_flat [2 * mix_flat.numel()]."""
+        B = len(lens)
+        c_off = (C.c_int64 * B)(*offs)
+        c_len = (C.c_int64 * B)(*lens)
+        with torch.cuda.device(self.device):
+            ws = self._workspace_for(c_len, B, precision)
+            est = torch.zeros(2 * mix_flat.numel(), dtype=torch.float32, device=self.device) \
+                if _needs_zero_fill(offs, lens, mix_flat.numel()) else \
+                torch.empty(2 * mix_flat.numel(), dtype=torch.float32, device=self.device)
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            if debug is None:
+                rc = self.lib.resep_forward(self.handle, mix_flat.data_ptr(), c_off, c_len, B, est.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), precision, batch_mode, stream)
+            else:
+                chunks = sum(((t - 16) // 8 + 1) // 150 + 1 for t in lens)
+                for name, rows in (("enc", chunks * 150), ("seg0", chunks * 150), ("chunk_mean", chunks),
+                                   ("mem0", chunks), ("seg1", chunks * 150)):
+                    debug[name] = torch.empty(rows, 128, dtype=torch.float32, device=self.device)
+                dbg = _lib.ResepDebugOut(*[C.cast(debug[n].data_ptr(), C.POINTER(C.c_float))
+                                           for n in ("enc", "seg0", "chunk_mean", "mem0", "seg1")])
+                rc = self.lib.resep_forward_debug(self.handle, mix_flat.data_ptr(), c_off, c_len, B, est.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), precision, batch_mode, stream,
+                                                  C.byref(dbg))
+            _lib.check(self.lib, self.handle, rc)
+        return est
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.resep_destroy(self.handle)
+            self.handle = C.c_void_p()
+        with _ENGINES_LOCK:
+            _ENGINES.pop(getattr(self, "id", -1), None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _needs_zero_fill(offs, lens, total) -> bool:
+    """True when the items do not tile the flat buffer exactly (gaps would stay uninitialised)."""
+    pos = 0
+    for o, n in sorted(zip(offs, lens)):
+        if o != pos:
+            return True
+        pos = o + n
+    return pos != total
+
+
+# ---------------------------------------------------------------------------------------------
+# the thin PyTorch custom op (CUDA dispatch key only -- a CPU tensor finds no kernel and raises)
+@torch.library.custom_op("clearconverse_b200::resep_separate", mutates_args=(), device_types="cuda")
+def _resep_separate(mix_flat: torch.Tensor, offs: list[int], lens: list[int], engine: int, precision: int,
+                    batch_mode: int) -> torch.Tensor:
+    eng = _ENGINES.get(engine)
+    if eng is None:
+        raise RuntimeError("clearconverse_b200: separator engine was destroyed")
+    return eng.forward(mix_flat, offs, lens, precision, batch_mode)
+
+
+@_resep_separate.register_fake
+def _(mix_flat, offs, lens, engine, precision, batch_mode):
+    return mix_flat.new_empty(2 * mix_flat.numel())
+
+
+# ---------------------------------------------------------------------------------------------
+class _Component:
+    """Stand-in for ``separator.mods.<name>``: holds that component's state dict."""
+
+    def __init__(self, owner, name):
+        self._owner, self._name = owner, name
+
+    def state_dict(self):
+        return dict(self._owner._sds[self._name])
+
+
+class SepformerSeparation:
+    """B200-native RE-SepFormer separator with upstream's inference surface.
+
+    precision: "fp32" (FMA kernels), "tf32" or "bf16" (tcgen05 GEMMs, fp32 accumulate);
+    batch_mode: "coupled" = upstream's literal batched semantics, "independent" = per item
+    (== looping B=1, what the product does).  For B == 1 the two coincide.
+    """
+
+    def __init__(self, state_dicts: dict, device="cuda", precision: str | None = None,
+                 batch_mode: str = "coupled", pe_rows: int = _weights.DEFAULT_PE_ROWS):
+        precision = precision or os.environ.get("RESEP_PRECISION", "tf32")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
+        if batch_mode not in _lib.BATCH_MODES:
+            raise ValueError(f"batch_mode must be one of {list(_lib.BATCH_MODES)}")
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.precision, self.batch_mode, self._pe_rows = precision, batch_mode, pe_rows
+        self._sds = {c: {k: v.detach().to("cpu", torch.float32).clone() for k, v in sd.items()
+                         if not k.endswith("pos_enc.pe")} for c, sd in state_dicts.items()}
+        self._engine = _Engine(self._sds, self.device, pe_rows)
+        self.hparams = SimpleNamespace(num_spks=NUM_SPKS, sample_rate=SAMPLE_RATE)
+        self.mods = SimpleNamespace(encoder=_Component(self, "encoder"), masknet=_Component(self, "masknet"),
+                                    decoder=_Component(self, "decoder"))
+
+    # ----------------------------------------------------------------------------- construction
+    @classmethod
+    def from_hparams(cls, source: str, savedir: str | None = None, run_opts: dict | None = None,
+                     hparams_file: str = "hyperparams.yaml", random_init_seed: int | None = None, **kwargs):
+        """Mirror of ``Pretrained.from_hparams`` for api.py:713-717.  Checkpoints are looked up in
+        ``savedir`` then in ``source`` (when it is a local directory).  There is no network on
+        the target hosts, so a hub id with no local copy raises unless ``random_init_seed`` (or
+        the env var RESEP_RANDOM_INIT_SEED) explicitly asks for random weights."""
+        device = (run_opts or {}).get("device", "cuda" if torch.cuda.is_available() else "cpu")
+        sds = None
+        for d in (savedir, source):
+            if d and os.path.isdir(d):
+                sds = _weights.load_checkpoint_dir(d)
+                if sds is not None:
+                    break
+        if sds is None:
+            seed = random_init_seed if random_init_seed is not None else os.environ.get("RESEP_RANDOM_INIT_SEED")
+            if seed is None:
+                raise FileNotFoundError(
+                    f"no encoder.ckpt/masknet.ckpt/decoder.ckpt under savedir={savedir!r} or source={source!r} "
+                    "and no network to fetch them; pass random_init_seed=... for random weights")
+            sds = _weights.random_init_state_dicts(int(seed))
+        return cls(sds, device=device, precision=kwargs.get("precision"),
+                   batch_mode=kwargs.get("batch_mode", "coupled"))
+
+    # ------------------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict: dict, strict: bool = True):
+        """``nn.Module.load_state_dict`` semantics over keys ``mods.<component>.<param>``.
+
+        api.py:738-745 passes ``{'masknet': sd, 'encoder': sd, 'decoder': sd}`` with
+        ``strict=False``; for upstream's nn.Module those three keys are simply *unexpected* and
+        silently ignored, so this must not raise and changes nothing.  Use
+        ``load_component_state_dicts`` to really apply fine-tuned checkpoints."""
+        own = {f"mods.{c}.{k}": (c, k) for c, sd in self._sds.items() for k in sd}
+        unexpected = [k for k in state_dict if k not in own and not k.endswith("pos_enc.pe")]
+        missing = [k for k in own if k not in state_dict]
+        if strict and (unexpected or missing):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {len(missing)} key(s), "
+                               f"unexpected key(s) {unexpected[:5]}")
+        hits = {k: v for k, v in state_dict.items() if k in own}
+        if hits:
+            new = {c: dict(sd) for c, sd in self._sds.items()}
+            for k, v in hits.items():
+                c, name = own[k]
+                if tuple(v.shape) != tuple(new[c][name].shape):
+                    raise RuntimeError(f"size mismatch for {k}")
+                new[c][name] = v.detach().to("cpu", torch.float32).clone()
+            self._apply(new)
+        return _IncompatibleKeys(missing, unexpected)
+
+    def load_component_state_dicts(self, state_dicts: dict):
+        """Apply ``{'encoder': sd, 'masknet': sd, 'decoder': sd}`` (any subset) for real."""
+        new = {c: dict(sd) for c, sd in self._sds.items()}
+        for c, sd in state_dicts.items():
+            if c not in new:
+                raise KeyError(c)
+            for k, v in sd.items():
+                if k.endswith("pos_enc.pe"):
+                    continue
+                new[c][k] = v.detach().to("cpu", torch.float32).clone()
+        self._apply(new)
+
+    def _apply(self, new):
+        _weights.validate_state_dicts(new)
+        self._engine.reload(new, self._pe_rows)
+        self._sds = new
+
+    def state_dict(self):
+        return {f"mods.{c}.{k}": v for c, sd in self._sds.items() for k, v in sd.items()}
+
+    # ------------------------------------------------------------------------------ inference
+    def _check_mix(self, mix):
+        if not isinstance(mix, torch.Tensor):
+            raise TypeError("mix must be a torch.Tensor")
+        if mix.dim() != 2:
+            raise RuntimeError(f"Expected a [batch, time] mixture, got shape {tuple(mix.shape)}")
+        if mix.dtype != torch.float32:
+            raise RuntimeError(f"expected a float32 mixture (the model weights are float32), got {mix.dtype}")
+        if mix.size(0) == 0:
+            raise RuntimeError("empty batch")
+        if mix.size(1) < KERNEL_SIZE:
+            raise RuntimeError(f"Calculated padded input size per channel: ({mix.size(1)}). Kernel size: (16). "
+                               "Kernel size can't be greater than actual input size")
+
+    @torch.no_grad()
+    def separate_batch(self, mix: torch.Tensor) -> torch.Tensor:
+        """mix [B,T] float32 (any device) -> est_sources [B,T,n_spk] float32 on ``self.device``."""
+        self._check_mix(mix)
+        B, T = mix.shape
+        mix = mix.to(self.device).contiguous()
+        est = torch.ops.clearconverse_b200.resep_separate(
+            mix.view(-1), [b * T for b in range(B)], [T] * B, self._engine.id,
+            _lib.PRECISIONS[self.precision], _lib.BATCH_MODES[self.batch_mode])
+        return est.view(B, T, NUM_SPKS)
+
+    forward = separate_batch
+    __call__ = separate_batch
+
+    @torch.no_grad()
+    def separate_segments(self, segments: list[torch.Tensor]) -> list[torch.Tensor]:
+        """Ragged batch: 1-D (or [1,T]) float32 segments of different lengths in ONE launch
+        sequence, each separated independently (== one ``separate_batch`` call per segment, the
+        way api.py:1073-1077 loops).  Returns a list of [T_i, n_spk] tensors on ``self.device``."""
+        flat, offs, lens, pos = [], [], [], 0
+        for s in segments:
+            s = s.reshape(-1)
+            if s.dtype != torch.float32:
+                raise RuntimeError(f"expected float32 segments, got {s.dtype}")
+            if s.numel() < KERNEL_SIZE:
+                raise RuntimeError("Kernel size can't be greater than actual input size")
+            flat.append(s.to(self.device, non_blocking=True))
+            offs.append(pos)
+            lens.append(s.numel())
+            pos += s.numel()
+        if not flat:
+            return []
+        est = torch.ops.clearconverse_b200.resep_separate(
+            torch.cat(flat), offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT)
+        return [est[2 * o:2 * (o + n)].view(n, NUM_SPKS) for o, n in zip(offs, lens)]
+
+    def separate_batch_debug(self, mix: torch.Tensor) -> tuple[torch.Tensor, dict]:
+        """separate_batch + intermediates (encoder / block outputs) for per-kernel parity tests."""
+        self._check_mix(mix)
+        B, T = mix.shape
+        mix = mix.to(self.device).contiguous()
+        dbg: dict = {}
+        est = self._engine.forward(mix.view(-1), [b * T for b in range(B)], [T] * B,
+                                   _lib.PRECISIONS[self.precision], _lib.BATCH_MODES[self.batch_mode], dbg)
+        return est.view(B, T, NUM_SPKS), dbg
+
+    def separate_file(self, path: str, savedir: str | None = None) -> torch.Tensor:
+        """Upstream's convenience wrapper: load, mono-mix, resample to 8 kHz, separate, and
+        peak-normalise each source."""
+        import torchaudio
+        batch, fs = torchaudio.load(path)
+        batch = batch.mean(dim=0, keepdim=True).to(self.device)
+        if fs != SAMPLE_RATE:
+            batch = torchaudio.functional.resample(batch, fs, SAMPLE_RATE)
+        est = self.separate_batch(batch.float())
+        return est / est.abs().max(dim=1, keepdim=True)[0]
+
+    def launch_count(self) -> int:
+        return self._engine.launch_count()
+
+    def close(self):
+        self._engine.close()

@@ -1,0 +1,118 @@
+"""Host-side sharding of independent overlap segments across the GPUs of one box.
+
+Every ``separate_batch`` call in the product is one segment with B=1
+(/root/reference/back/api.py:1073-1077) and segments share nothing but the weights, so the
+path shards by units with NO data-path collective: weights are replicated,
+segments are length-bucketed (bucket = number of 150-frame chunks, i.e. 1,200-sample steps),
+buckets are cut into batches under a token budget, batches are dealt to ranks greedily by
+algorithmic FLOPs, and results are gathered on the host into segment order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+KSZ, STRIDE, CHUNK = 16, 8, 150
+FLOP_PER_INTRA_TOKEN = 11_714_560          # 16 intra layers x 732,160
+FLOP_PER_FRAME_ENDS = 78_080               # encoder + output_fc + mask-mul + decoder
+FLOP_MEM_CHUNK_BASE = 8 * 655_360          # memory transformer, per chunk, GEMM part
+FLOP_MEM_CHUNK_PER_SEQ = 8 * 512           # ... attention part, per chunk per sequence element
+
+
+def frames_of(T: int) -> int:
+    return (T - KSZ) // STRIDE + 1
+
+
+def chunks_of(T: int) -> int:
+    return frames_of(T) // CHUNK + 1
+
+
+def flops_of(T: int, mem_seq_len: int | None = None) -> int:
+    """Algorithmic FLOPs of separating one T-sample segment (multiply-add = 2)."""
+    L, S = frames_of(T), chunks_of(T)
+    s_seq = S if mem_seq_len is None else mem_seq_len
+    return S * CHUNK * FLOP_PER_INTRA_TOKEN + L * FLOP_PER_FRAME_ENDS + S * (FLOP_MEM_CHUNK_BASE + FLOP_MEM_CHUNK_PER_SEQ * s_seq)
+
+
+@dataclass
+class Batch:
+    indices: list[int] = field(default_factory=list)   # positions in the caller's segment list
+    lens: list[int] = field(default_factory=list)
+    chunks: int = 0
+    flops: int = 0
+
+
+def bucket_segments(lens: list[int], max_chunks_per_batch: int = 2048) -> list[Batch]:
+    """Group segments of similar length into batches of at most ``max_chunks_per_batch`` chunks
+    (150 frames each; 2048 chunks = 307,200 token rows ~ 2.8 GB of fp32 workspace).  Segments
+    are sorted by chunk count so a batch holds near-equal lengths; a segment longer than the
+    budget gets a batch of its own."""
+    order = sorted(range(len(lens)), key=lambda i: (chunks_of(lens[i]), lens[i], i), reverse=True)
+    batches, cur = [], Batch()
+    for i in order:
+        s = chunks_of(lens[i])
+        if cur.indices and cur.chunks + s > max_chunks_per_batch:
+            batches.append(cur)
+            cur = Batch()
+        cur.indices.append(i)
+        cur.lens.append(lens[i])
+        cur.chunks += s
+        cur.flops += flops_of(lens[i])
+    if cur.indices:
+        batches.append(cur)
+    return batches
+
+
+def assign_to_ranks(batches: list[Batch], world_size: int) -> list[list[int]]:
+    """Longest-processing-time greedy: batches by descending FLOPs, each to the least-loaded
+    rank.  Returns, per rank, the list of batch indices it runs."""
+    load = [0] * world_size
+    out: list[list[int]] = [[] for _ in range(world_size)]
+    for b in sorted(range(len(batches)), key=lambda j: batches[j].flops, reverse=True):
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        out[r].append(b)
+        load[r] += batches[b].flops
+    return out
+
+
+def plan_shards(lens: list[int], world_size: int, max_chunks_per_batch: int = 2048, batches_per_rank: int = 4):
+    """(batches, per-rank batch indices).  With more than one rank the batch budget is lowered to
+    about total/(world_size * batches_per_rank) chunks so the greedy deal can balance the ranks."""
+    budget = max_chunks_per_batch
+    if world_size > 1:
+        total_chunks = sum(chunks_of(t) for t in lens)
+        budget = max(1, min(budget, -(-total_chunks // (world_size * batches_per_rank))))
+    batches = bucket_segments(lens, budget)
+    return batches, assign_to_ranks(batches, world_size)
+
+
+def separate_sharded(segments, separate_fn, rank: int = 0, world_size: int = 1, group=None,
+                     max_chunks_per_batch: int = 2048, gather: bool = True):
+    """Run this rank's share of ``segments`` (list of 1-D float32 tensors) through
+    ``separate_fn(list_of_segments) -> list of [T_i, n_spk] tensors`` and, if ``gather``,
+    collect all results on rank 0 in the original order (host-side gather, no NCCL).
+
+    Returns (results or None on non-zero ranks, audio samples this rank processed)."""
+    lens = [int(s.numel()) for s in segments]
+    batches, per_rank = plan_shards(lens, world_size, max_chunks_per_batch)
+    mine: dict[int, object] = {}
+    samples = 0
+    for b in per_rank[rank]:
+        idx = batches[b].indices
+        outs = separate_fn([segments[i] for i in idx])
+        for i, o in zip(idx, outs):
+            mine[i] = o
+            samples += lens[i]
+    if not gather:
+        return mine, samples
+    if world_size == 1:
+        return [mine[i] for i in range(len(segments))], samples
+    import torch.distributed as dist
+    payload = {i: o.detach().cpu() for i, o in mine.items()}
+    gathered = [None] * world_size if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0, group=group)
+    if rank != 0:
+        return None, samples
+    merged = {}
+    for part in gathered:
+        merged.update(part)
+    return [merged[i] for i in range(len(segments))], samples

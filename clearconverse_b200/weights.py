@@ -1,0 +1,149 @@
+"""Weight containers of the RE-SepFormer path.
+
+Upstream saves three checkpoints (/root/reference/back/api.py:729): ``encoder.ckpt``,
+``masknet.ckpt``, ``decoder.ckpt`` -- plain ``state_dict``s with the key names listed in
+SURVEY.md section 8(a12).  This module (1) packs such dicts into the ``ResepWeights`` struct of
+the C ABI, (2) loads them from a directory, and (3) creates random-init dicts of the same
+architecture for benchmarking when no checkpoint is reachable (there is no network here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+
+from . import _lib
+
+D, KSZ, FFN, NL, NSPK, CHUNK = 128, 16, 1024, 8, 2, 150
+DEFAULT_PE_ROWS = 8192          # >= longest memory sequence we expect (8192 chunks = 2.7 h of 8 kHz audio)
+CKPT_FILES = {"encoder": "encoder.ckpt", "masknet": "masknet.ckpt", "decoder": "decoder.ckpt"}
+
+
+def positional_table(rows: int) -> torch.Tensor:
+    """``pos_enc.pe`` rows: upstream stores this fp32 table as a module buffer
+    (speechbrain Transformer.py PositionalEncoding); same expression, evaluated in fp32."""
+    pe = torch.zeros(rows, D)
+    positions = torch.arange(0, rows).unsqueeze(1).float()
+    denominator = torch.exp(torch.arange(0, D, 2).float() * -(math.log(10000.0) / D))
+    pe[:, 0::2] = torch.sin(positions * denominator)
+    pe[:, 1::2] = torch.cos(positions * denominator)
+    return pe
+
+
+def _block_keys(prefix: str):
+    keys = {}
+    for l in range(NL):
+        p = f"{prefix}mdl.layers.{l}."
+        keys.update({
+            p + "self_att.att.in_proj_weight": (3 * D, D), p + "self_att.att.in_proj_bias": (3 * D,),
+            p + "self_att.att.out_proj.weight": (D, D), p + "self_att.att.out_proj.bias": (D,),
+            p + "pos_ffn.ffn.0.weight": (FFN, D), p + "pos_ffn.ffn.0.bias": (FFN,),
+            p + "pos_ffn.ffn.3.weight": (D, FFN), p + "pos_ffn.ffn.3.bias": (D,),
+            p + "norm1.norm.weight": (D,), p + "norm1.norm.bias": (D,),
+            p + "norm2.norm.weight": (D,), p + "norm2.norm.bias": (D,),
+        })
+    keys.update({prefix + "mdl.norm.norm.weight": (D,), prefix + "mdl.norm.norm.bias": (D,),
+                 prefix + "norm.weight": (D, 1), prefix + "norm.bias": (D, 1)})
+    return keys
+
+
+def expected_shapes() -> dict[str, dict[str, tuple]]:
+    """Key -> shape for the three component state dicts (upstream names)."""
+    mk = {}
+    for pfx in ("model.seg_model.0.", "model.seg_model.1.", "model.mem_model.0."):
+        mk.update(_block_keys(pfx))
+    mk.update({"model.output_fc.0.weight": (1,), "model.output_fc.1.weight": (NSPK * D, D, 1),
+               "model.output_fc.1.bias": (NSPK * D,)})
+    return {"encoder": {"conv1d.weight": (D, 1, KSZ)}, "masknet": mk, "decoder": {"weight": (D, 1, KSZ)}}
+
+
+def validate_state_dicts(sds: dict) -> None:
+    exp = expected_shapes()
+    for comp, shapes in exp.items():
+        if comp not in sds:
+            raise KeyError(f"missing component '{comp}'")
+        for k, shp in shapes.items():
+            if k not in sds[comp]:
+                raise KeyError(f"{comp}: missing key '{k}'")
+            if tuple(sds[comp][k].shape) != tuple(shp):
+                raise ValueError(f"{comp}.{k}: shape {tuple(sds[comp][k].shape)} != expected {shp}")
+
+
+def random_init_state_dicts(seed: int = 0) -> dict:
+    """Random weights of the resepformer-wsj02mix architecture (for benchmarks: throughput does
+    not depend on the values).  PyTorch-default-like scales; every affine / bias is perturbed
+    so no term is degenerate."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for comp, shapes in expected_shapes().items():
+        sd = {}
+        for k, shp in shapes.items():
+            if k.endswith("output_fc.0.weight"):
+                t = torch.full(shp, 0.25)
+            elif len(shp) == 3 or (len(shp) == 2 and shp[1] > 1):
+                fan_in = shp[1] * (shp[2] if len(shp) == 3 else 1)
+                if comp == "decoder":
+                    fan_in = KSZ
+                bound = 1.0 / math.sqrt(fan_in)
+                t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+            elif k.endswith("norm.weight") or k.endswith(".norm.weight"):
+                t = 1.0 + 0.05 * torch.randn(shp, generator=g)
+            else:
+                t = 0.05 * torch.randn(shp, generator=g)
+            sd[k] = t.float()
+        out[comp] = sd
+    return out
+
+
+def load_checkpoint_dir(path: str, map_location="cpu") -> dict | None:
+    """Load encoder.ckpt / masknet.ckpt / decoder.ckpt from ``path`` (api.py:729); None if absent."""
+    if not path or not all(os.path.exists(os.path.join(path, f)) for f in CKPT_FILES.values()):
+        return None
+    sds = {}
+    for comp, fname in CKPT_FILES.items():
+        sd = torch.load(os.path.join(path, fname), map_location=map_location, weights_only=True)
+        sds[comp] = {k: v for k, v in sd.items() if not k.endswith("pos_enc.pe")}   # 51 MB buffers, regenerated
+    return sds
+
+
+class PackedWeights:
+    """ResepWeights struct + the fp32 CPU tensors its pointers refer to (kept alive here)."""
+
+    def __init__(self, sds: dict, pe_rows: int = DEFAULT_PE_ROWS):
+        validate_state_dicts(sds)
+        self._keep = []
+        self.struct = _lib.ResepWeights()
+        w = self.struct
+
+        def ptr(t: torch.Tensor):
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            self._keep.append(t)
+            return C.cast(t.data_ptr(), C.POINTER(C.c_float))
+
+        enc, mk, dec = sds["encoder"], sds["masknet"], sds["decoder"]
+        w.enc_w = ptr(enc["conv1d.weight"])
+        w.dec_w = ptr(dec["weight"])
+        w.prelu_a = ptr(mk["model.output_fc.0.weight"])
+        w.fc_w = ptr(mk["model.output_fc.1.weight"])
+        w.fc_b = ptr(mk["model.output_fc.1.bias"])
+        w.pe = ptr(positional_table(pe_rows))
+        w.pe_rows = pe_rows
+        for dst, pfx in ((w.seg[0], "model.seg_model.0."), (w.seg[1], "model.seg_model.1."),
+                         (w.mem[0], "model.mem_model.0.")):
+            for l in range(NL):
+                p, lw = f"{pfx}mdl.layers.{l}.", dst.layers[l]
+                lw.norm1_w, lw.norm1_b = ptr(mk[p + "norm1.norm.weight"]), ptr(mk[p + "norm1.norm.bias"])
+                lw.in_proj_w, lw.in_proj_b = ptr(mk[p + "self_att.att.in_proj_weight"]), ptr(mk[p + "self_att.att.in_proj_bias"])
+                lw.out_proj_w, lw.out_proj_b = ptr(mk[p + "self_att.att.out_proj.weight"]), ptr(mk[p + "self_att.att.out_proj.bias"])
+                lw.norm2_w, lw.norm2_b = ptr(mk[p + "norm2.norm.weight"]), ptr(mk[p + "norm2.norm.bias"])
+                lw.ffn1_w, lw.ffn1_b = ptr(mk[p + "pos_ffn.ffn.0.weight"]), ptr(mk[p + "pos_ffn.ffn.0.bias"])
+                lw.ffn2_w, lw.ffn2_b = ptr(mk[p + "pos_ffn.ffn.3.weight"]), ptr(mk[p + "pos_ffn.ffn.3.bias"])
+            dst.final_norm_w, dst.final_norm_b = ptr(mk[pfx + "mdl.norm.norm.weight"]), ptr(mk[pfx + "mdl.norm.norm.bias"])
+            dst.gln_w, dst.gln_b = ptr(mk[pfx + "norm.weight"]), ptr(mk[pfx + "norm.bias"])
+
+
+def default_config() -> "_lib.ResepConfig":
+    return _lib.ResepConfig(abi_version=_lib.ABI_VERSION, n_filters=D, kernel_size=KSZ, stride=KSZ // 2,
+                            segment_size=CHUNK, n_heads=8, d_ffn=FFN, n_layers=NL, n_blocks=2, n_spks=NSPK)

@@ -1,0 +1,141 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol,
+weight packing, synthetic data, bucketing / sharding (incl. world_size-2 gloo), loud failure
+without a GPU."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from clearconverse_b200 import _lib, sharding, synth, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(cuda_lib_built):
+    header = open(os.path.join(ROOT, "include", "resep_b200.h")).read()
+    declared = set(re.findall(r"\b(resep_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert hasattr(cuda_lib_built, name), name
+
+
+def test_library_has_only_sm100a_code(cuda_lib_built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_fails_loudly(sds):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from clearconverse_b200 import SepformerSeparation
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SepformerSeparation(sds, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback|No CUDA|no CUDA"):
+        SepformerSeparation(sds, device="cuda")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "clearconverse_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/" not in src or f.endswith((".cu", ".cuh")), f
+
+
+def test_weight_packing_roundtrip(sds):
+    pw = weights.PackedWeights(sds, pe_rows=256)
+    w = pw.struct
+    k = "model.mem_model.0.mdl.layers.5.pos_ffn.ffn.3.weight"
+    got = torch.tensor([w.mem[0].layers[5].ffn2_w[i] for i in range(16)])
+    assert torch.equal(got, sds["masknet"][k].reshape(-1)[:16])
+    assert w.pe_rows == 256 and abs(w.pe[1] - 1.0) < 1e-7          # pe[0,1] = cos(0)
+    bad = {c: dict(sd) for c, sd in sds.items()}
+    bad["masknet"].pop("model.output_fc.1.bias")
+    with pytest.raises(KeyError):
+        weights.PackedWeights(bad)
+
+
+def test_random_init_has_upstream_keys_and_count():
+    sd = weights.random_init_state_dicts(0)
+    weights.validate_state_dicts(sd)
+    assert sum(v.numel() for c in sd.values() for v in c.values()) == 7_955_201
+    sd2 = weights.random_init_state_dicts(0)
+    assert all(torch.equal(sd["masknet"][k], sd2["masknet"][k]) for k in sd["masknet"])
+
+
+def test_checkpoint_dir_roundtrip(tmp_path, sds):
+    for comp, fname in weights.CKPT_FILES.items():
+        d = dict(sds[comp])
+        if comp == "masknet":
+            d["model.seg_model.0.pos_enc.pe"] = torch.zeros(1, 4, 128)     # upstream ckpts carry this buffer
+        torch.save(d, tmp_path / fname)
+    back = weights.load_checkpoint_dir(str(tmp_path))
+    weights.validate_state_dicts(back)
+    assert "model.seg_model.0.pos_enc.pe" not in back["masknet"]
+    assert weights.load_checkpoint_dir(str(tmp_path / "nope")) is None
+
+
+def test_synth_is_deterministic_and_normalised():
+    a, b = synth.synth_batch(2, 4000, 3), synth.synth_batch(2, 4000, 3)
+    assert torch.equal(a, b) and a.dtype == torch.float32
+    assert torch.allclose(a.abs().amax(dim=1), torch.ones(2))
+    segs = synth.meeting_overlap_segments(720.0)
+    assert abs(sum(segs) / 8000 - 720.0) < 1.0 and min(segs) >= 16 and max(segs) <= 30 * 8000 + 1
+
+
+def test_flops_match_survey_figures():
+    # config 1 = 47.9 GFLOP, config 3 (60 s) = 710 GFLOP
+    assert abs(sharding.flops_of(32000) / 1e9 - 47.9) < 0.2
+    assert abs(sharding.flops_of(480000) / 1e9 - 710) < 3
+    assert sharding.chunks_of(32000) == 27 and sharding.chunks_of(480000) == 400 and sharding.chunks_of(16 + 8 * 149) == 2
+
+
+def test_bucketing_and_assignment_cover_everything_once():
+    lens = synth.meeting_overlap_segments(720.0)
+    for ws in (1, 2, 4, 8):
+        batches, per_rank = sharding.plan_shards(lens, ws, 512)
+        seen = sorted(i for b in batches for i in b.indices)
+        assert seen == list(range(len(lens)))
+        assert sorted(b for r in per_rank for b in r) == list(range(len(batches)))
+        assert all(b.chunks <= 512 or len(b.indices) == 1 for b in batches)
+        if ws == 1:
+            continue
+        load = [sum(batches[b].flops for b in r) for r in per_rank]
+        assert max(load) <= 1.15 * (sum(load) / ws), (ws, load)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    segs = [torch.full((n,), float(i)) for i, n in enumerate([4000, 1600, 32000, 900, 12000, 16, 2400])]
+
+    def fake_separate(batch):            # stands in for the CUDA engine: host logic only
+        return [torch.stack([s + 1, s - 1], dim=-1) for s in batch]
+
+    res, samples = sharding.separate_sharded(segs, fake_separate, rank, world)
+    total = torch.tensor([samples])
+    dist.all_reduce(total)
+    if rank == 0:
+        ok = all(torch.equal(r, torch.stack([s + 1, s - 1], dim=-1)) for r, s in zip(res, segs))
+        q.put((ok, int(total.item()), sum(s.numel() for s in segs)))
+    else:
+        assert res is None
+    dist.destroy_process_group()
+
+
+def test_sharded_driver_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    ok, total, want = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert ok and total == want and all(p.exitcode == 0 for p in procs)
