@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* _
                                                         const int* __restrict__ seq_off) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
-  __shared__ float colsum[8][D];
+  __shared__ __align__(16) float colsum[8][D];
   const int seq = blockIdx.x;
   int off, len;
   if (seq_off != nullptr) {
