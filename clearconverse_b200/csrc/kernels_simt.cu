@@ -150,6 +150,16 @@ __device__ __forceinline__ void store4(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+struct tf32_t { float v; };   // tag type: fp32 storage holding tf32-rounded values
+__device__ __forceinline__ void store4(tf32_t* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ b, OutT* __restrict__ y, int64_t rows) {
@@ -171,6 +181,24 @@ int launch_layernorm(ResepHandle* h, const float* x, const float* w, const float
 }
 template int launch_layernorm<float>(ResepHandle*, const float*, const float*, const float*, float*, int64_t, cudaStream_t);
 template int launch_layernorm<bf16>(ResepHandle*, const float*, const float*, const float*, bf16*, int64_t, cudaStream_t);
+int launch_layernorm_tf32(ResepHandle* h, const float* x, const float* w, const float* b, float* y, int64_t rows,
+                          cudaStream_t st) {
+  return launch_layernorm<tf32_t>(h, x, w, b, reinterpret_cast<tf32_t*>(y), rows, st);
+}
+
+__global__ void k_round_tf32(float* x, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<float4*>(x)[i];
+  reinterpret_cast<float4*>(x)[i] = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+}
+int launch_round_tf32(ResepHandle* h, float* x, int64_t n, cudaStream_t st) {
+  const int64_t n4 = n / 4;
+  if (n4 == 0) return RESEP_OK;
+  k_round_tf32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, n4);
+  RESEP_LAUNCH_CHECK(h, "k_round_tf32");
+  return RESEP_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // fp32 GEMM  C[M,N] = A[M,K] . W[N,K]^T + bias (+relu) (+residual).  64x64x16 tiles, 256 threads,

@@ -1,8 +1,559 @@
+// Tensor-core kernels of the RE-SepFormer path (sm_100a only).
+//
+//  * k_gemm_tc     persistent, warp-specialised GEMM  out = epi(A[M,K] . W[N,K]^T + bias):
+//                  TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma
+//                  (cta_group::1, M=128 x N=128 per instruction, kind::f16 for bf16 operands or
+//                  kind::tf32) -> double-buffered fp32 accumulators in TMEM -> tcgen05.ld epilogue
+//                  (bias, ReLU, residual add, bf16 / tf32 rounding) overlapped with the next tile's MMAs.
+//  * k_attention_bf16  per (sequence tile, head) softmax(q k^T / 4) v with bf16 mma.sync and fp32
+//                  online softmax; head_dim is 16, so the kernel is exp/softmax-bound, not MMA-bound.
+//
+// Upstream arithmetic restated (speechbrain Transformer.py TransformerEncoderLayer, pre-norm):
+//   y = LN1(x); x += OutProj(MHA(y)); y = LN2(x); x += W2 relu(W1 y + b1) + b2
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+
+#include "ptx_sm100.cuh"
 #include "resep_tc.cuh"
+
 namespace resep {
-int tc_init(ResepHandle* h) { return set_err(h, RESEP_EINVAL, "tensor-core path not built yet"); }
-void tc_destroy(ResepHandle*) {}
-int tc_run_layer(ResepHandle* h, const LayerDev&, float*, int64_t, int, int, const int*, const int*, const int*, int, float*, float*, float*, float*, int, cudaStream_t) { return set_err(h, RESEP_EINVAL, "tensor-core path not built yet"); }
-int tc_run_mask(ResepHandle* h, const float*, float*, float*, int64_t, int, cudaStream_t) { return set_err(h, RESEP_EINVAL, "tensor-core path not built yet"); }
-int tc_linear_test(ResepHandle* h, const float*, const float*, const float*, float*, int64_t, int, int, bool, int, cudaStream_t) { return set_err(h, RESEP_EINVAL, "tensor-core path not built yet"); }
+
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+struct TcState {
+  int dummy = 0;
+};
+
+int tc_init(ResepHandle* h) {
+  if (h->tc_ready) return RESEP_OK;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  h->tc_ready = true;
+  return RESEP_OK;
 }
+
+void tc_destroy(ResepHandle* h) { h->tc_ready = false; }
+
+// 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes of columns], 128B swizzle, OOB -> 0.
+template <typename T>
+static int make_tmap(ResepHandle* h, CUtensorMap* m, const T* base, int64_t rows, int cols, int box_rows) {
+  const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(T)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, dt, 2, const_cast<T*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return RESEP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM
+constexpr int BM = 128, BN = 128;
+constexpr int STAGES = 4;
+constexpr int STAGE_A_BYTES = BM * 128;               // 128 rows x 128 B of K
+constexpr int STAGE_B_BYTES = BN * 128;
+constexpr int stage_bytes(bool split_w) { return STAGE_A_BYTES + (split_w ? 2 : 1) * STAGE_B_BYTES; }
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;            // 256 fp32 columns
+constexpr int GEMM_THREADS = 192;                     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int gemm_smem(bool split_w) { return STAGES * stage_bytes(split_w) + 1024 /*alignment slack*/ + 256 /*barriers*/; }
+
+enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2, EPI_STORE_TF32 = 3 };
+
+// SPLITW (tf32 only): the weight is given as two tf32 matrices W = W_hi + W_lo and every K-slice issues two
+// MMAs into the same accumulator; this removes the weight-rounding error, which dominates plain TF32
+// (measured: max-abs 8e-4 -> 2e-4 on the forward pass), at the cost of one more B tile per stage.
+// (Mixing a bf16 A with an fp16 B in one kind::f16 MMA was tried for the same purpose: it raises an
+// illegal-instruction fault on sm_100a, so both operands always share one format.)
+template <typename TIn, int EPI, bool SPLITW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, void* out_, int64_t M, int N, int K,
+          int relu) {
+  constexpr int STAGE_BYTES = stage_bytes(SPLITW);
+  constexpr int BK = 128 / sizeof(TIn);               // elements per 128-byte swizzle row: 64 bf16 / 32 tf32
+  constexpr int UK = 32 / sizeof(TIn);                // K per tcgen05.mma: 16 bf16 / 8 tf32
+  constexpr uint32_t FMT = sizeof(TIn) == 2 ? UMMA_BF16 : UMMA_TF32;
+  constexpr uint32_t IDESC = umma_idesc(FMT, FMT, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                          // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;                // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;             // [ACC_STAGES]
+  uint64_t* acc_empty = bars + 2 * STAGES + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = N / BN;
+  const int m_tiles = (int)((M + BM - 1) / BM);
+  const int total_tiles = m_tiles * n_tiles;
+  const int kblocks = K / BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if constexpr (SPLITW) prefetch_tmap(&tmWlo);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sa + STAGE_A_BYTES, &tmW, &full_bar[stage], kb * BK, n0);
+          if constexpr (SPLITW) tma_load_2d(sa + STAGE_A_BYTES + STAGE_B_BYTES, &tmWlo, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + STAGE_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 -> +2)
+            if constexpr (sizeof(TIn) == 2)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            else
+              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          if constexpr (SPLITW) {
+            const uint64_t ldesc = umma_desc_k_sw128(sa + STAGE_A_BYTES + STAGE_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              if constexpr (sizeof(TIn) == 2) umma_bf16(d_tmem, adesc + 2 * k, ldesc + 2 * k, IDESC, true);
+              else umma_tf32(d_tmem, adesc + 2 * k, ldesc + 2 * k, IDESC, true);
+            }
+          }
+          umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);                   // accumulator ready for the epilogue
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- epilogue (4 warps, one row per thread)
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (row < M) {
+          const float* bp = bias + n0 + c0;
+          if constexpr (EPI == EPI_STORE_BF16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_) + row * N + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[i] = __uint_as_float(v[j + i]) + __ldg(bp + j + i);
+                if (relu) f[i] = fmaxf(f[i], 0.f);
+              }
+              op[j / 8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                     pack_bf16(f[6], f[7]));
+            }
+          } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + row * N + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float f[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[i] = __uint_as_float(v[j + i]) + __ldg(bp + j + i);
+                if (relu) f[i] = fmaxf(f[i], 0.f);
+                if constexpr (EPI == EPI_STORE_TF32) f[i] = round_tf32(f[i]);
+              }
+              if constexpr (EPI == EPI_RESID_F32) {
+                const float4 r = op[j / 4];
+                f[0] += r.x; f[1] += r.y; f[2] += r.z; f[3] += r.w;
+              }
+              op[j / 4] = make_float4(f[0], f[1], f[2], f[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <typename TIn, int EPI, bool SPLITW = false>
+static int launch_gemm_tc(ResepHandle* h, const TIn* A, const TIn* W, const float* bias, void* out, int64_t M, int N,
+                          int K, bool relu, cudaStream_t st, const TIn* Wlo = nullptr) {
+  if (M <= 0) return RESEP_OK;
+  constexpr int BK = 128 / sizeof(TIn);
+  if (N % BN != 0 || K % BK != 0) return set_err(h, RESEP_EINVAL, "gemm_tc: N % 128 or K % (128 B) != 0");
+  CUtensorMap tmA, tmW, tmWlo;
+  int rc;
+  if ((rc = make_tmap<TIn>(h, &tmA, A, M, K, BM))) return rc;
+  if ((rc = make_tmap<TIn>(h, &tmW, W, N, K, BN))) return rc;
+  if ((rc = make_tmap<TIn>(h, &tmWlo, SPLITW ? Wlo : W, N, K, BN))) return rc;
+  constexpr int GEMM_SMEM = gemm_smem(SPLITW);
+  auto kern = k_gemm_tc<TIn, EPI, SPLITW>;
+  RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, tmWlo, bias, out, M, N, K, relu ? 1 : 0);
+  RESEP_LAUNCH_CHECK(h, "k_gemm_tc");
+  return RESEP_OK;
+}
+
+// bf16-activation GEMM with the handle's weight operand mode: 1 = W as bf16 hi + lo (default), 0 = bf16(W) only
+template <int EPI>
+static int gemm_bf16(ResepHandle* h, int mode, const bf16* A, const bf16* W, const bf16* Wlo, const float* bias, void* out,
+                     int64_t M, int N, int K, bool relu, cudaStream_t st) {
+  if (mode == 1) return launch_gemm_tc<bf16, EPI, true>(h, A, W, bias, out, M, N, K, relu, st, Wlo);
+  return launch_gemm_tc<bf16, EPI, false>(h, A, W, bias, out, M, N, K, relu, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention, bf16 mma.sync m16n8k16.  One CTA = 160 query rows (5 warps x 2 m16 tiles) of one
+// sequence for one head; keys/values are streamed through shared memory in tiles of 160 with an
+// online (running max / sum) softmax, so a 150-row chunk is a single pass and the memory
+// transformer's longer sequences loop.  K is staged row-major [key][16] (row stride 24 halves,
+// conflict-free B-fragment reads), V transposed [16][key] so that P.V B-fragments are 32-bit loads.
+constexpr int AKT = 160;        // keys per tile == queries per CTA
+constexpr int KS_STRIDE = 24;   // halves
+constexpr int VT_STRIDE = AKT + 8;
+__global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int seq_len,
+                                                        const int* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                        const int* __restrict__ tile_q0) {
+  __shared__ __align__(16) bf16 Ks[AKT * KS_STRIDE];
+  __shared__ __align__(16) bf16 Vt[DH * VT_STRIDE];
+  int q0, off, len;
+  if (tile_seq != nullptr) {
+    const int seq = tile_seq[blockIdx.x];
+    q0 = tile_q0[blockIdx.x];
+    off = seq_off[seq];
+    len = seq_off[seq + 1] - off;
+  } else {
+    const int tps = (seq_len + AKT - 1) / AKT;
+    q0 = (blockIdx.x % tps) * AKT;
+    off = (blockIdx.x / tps) * seq_len;
+    len = seq_len;
+  }
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
+
+  // Q fragments of this warp's two m16 tiles (rows beyond the sequence read as zero)
+  uint32_t qa[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = q0 + warp * 32 + mt * 16 + g;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = r0 + hh * 8;
+      uint32_t lo = 0, hi = 0;
+      if (r < len) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(qbase + (int64_t)r * (3 * D));
+        lo = p[t4];
+        hi = p[t4 + 4];
+      }
+      qa[mt][hh] = lo;
+      qa[mt][hh + 2] = hi;
+    }
+  }
+  float m_run[2][2], l_run[2][2], o[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      m_run[mt][hh] = -INFINITY;
+      l_run[mt][hh] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[mt][hh][i] = 0.f;   // o[mt][ntile][c]
+    }
+  constexpr float SCALE_LOG2E = 0.25f * 1.4426950408889634f;
+
+  for (int kt = 0; kt < len; kt += AKT) {
+    __syncthreads();
+    {  // stage one key/value row per thread
+      const int key = kt + threadIdx.x;
+      uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+      if (key < len) {
+        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
+        k0 = p[0]; k1 = p[1];
+        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
+        v0 = pv[0]; v1 = pv[1];
+      }
+      uint32_t* kd = reinterpret_cast<uint32_t*>(Ks + threadIdx.x * KS_STRIDE);
+      kd[0] = k0.x; kd[1] = k0.y; kd[2] = k0.z; kd[3] = k0.w; kd[4] = k1.x; kd[5] = k1.y; kd[6] = k1.z; kd[7] = k1.w;
+      const uint32_t vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&vv[i]);
+        Vt[(2 * i) * VT_STRIDE + threadIdx.x] = pr.x;
+        Vt[(2 * i + 1) * VT_STRIDE + threadIdx.x] = pr.y;
+      }
+    }
+    __syncthreads();
+    const int nvalid = min(AKT, len - kt);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (q0 + warp * 32 + mt * 16 >= len) continue;   // warp-uniform: whole m-tile is padding
+      float s[AKT / 8][4];
+#pragma unroll
+      for (int j = 0; j < AKT / 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const uint32_t* kp = reinterpret_cast<const uint32_t*>(Ks + (8 * j + g) * KS_STRIDE);
+        mma_bf16_16816(s[j], qa[mt], kp[t4], kp[t4 + 4]);
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < AKT / 8; ++j) {
+        const int c = 8 * j + 2 * t4;
+        s[j][0] = (c < nvalid) ? s[j][0] * SCALE_LOG2E : -INFINITY;
+        s[j][1] = (c + 1 < nvalid) ? s[j][1] * SCALE_LOG2E : -INFINITY;
+        s[j][2] = (c < nvalid) ? s[j][2] * SCALE_LOG2E : -INFINITY;
+        s[j][3] = (c + 1 < nvalid) ? s[j][3] * SCALE_LOG2E : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m_run[mt][0], mx0), mn1 = fmaxf(m_run[mt][1], mx1);
+      const float c0 = exp2f(m_run[mt][0] - mn0), c1 = exp2f(m_run[mt][1] - mn1);
+      m_run[mt][0] = mn0; m_run[mt][1] = mn1;
+      l_run[mt][0] *= c0; l_run[mt][1] *= c1;
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) { o[mt][nn][0] *= c0; o[mt][nn][1] *= c0; o[mt][nn][2] *= c1; o[mt][nn][3] *= c1; }
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < AKT / 8; ++j) {
+        s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
+        s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
+        ls0 += s[j][0] + s[j][1];
+        ls1 += s[j][2] + s[j][3];
+      }
+      l_run[mt][0] += ls0; l_run[mt][1] += ls1;
+#pragma unroll
+      for (int kk = 0; kk < AKT / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vt + (8 * nn + g) * VT_STRIDE + 16 * kk);
+          mma_bf16_16816(o[mt][nn], pa, vp[t4], vp[t4 + 4]);
+        }
+      }
+    }
+  }
+  // normalise and store: C fragment rows g / g+8, columns 2*t4, 2*t4+1 of each 8-wide dh tile
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float l = l_run[mt][hh];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const int r = q0 + warp * 32 + mt * 16 + hh * 8 + g;
+      if (r < len) {
+        const float inv = 1.f / l;
+        bf16* op = ctx + (int64_t)(off + r) * D + head * DH;
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn)
+          *reinterpret_cast<uint32_t*>(op + 8 * nn + 2 * t4) =
+              pack_bf16(o[mt][nn][2 * hh] * inv, o[mt][nn][2 * hh + 1] * inv);
+      }
+    }
+  }
+}
+
+static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
+                                 const int* tile_seq, const int* tile_q0, int n_tiles128, cudaStream_t st) {
+  // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
+  // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
+  // of the next tile with identical results).
+  if (tile_seq == nullptr) {
+    if (n_seq == 0) return RESEP_OK;
+    const int tps = (seq_len + AKT - 1) / AKT;
+    k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
+  } else {
+    if (n_tiles128 == 0) return RESEP_OK;
+    k_attention_bf16<<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
+  }
+  RESEP_LAUNCH_CHECK(h, "k_attention_bf16");
+  return RESEP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers: dtype conversion for the test hook
+template <typename OutT>
+__global__ void k_convert(const float* __restrict__ x, OutT* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if constexpr (sizeof(OutT) == 2) y[i] = __float2bfloat16_rn(x[i]);
+  else y[i] = round_tf32(x[i]);
+}
+
+__global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float h = round_tf32(w[i]);
+  hi[i] = h;
+  lo[i] = round_tf32(w[i] - h);
+}
+
+__global__ void k_split_w16(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bf16 h = __float2bfloat16_rn(w[i]);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(h));
+}
+
+int tc_linear_test(ResepHandle* h, const float* A, const float* W, const float* bias, float* out, int64_t M, int N, int K,
+                   bool relu, int precision, cudaStream_t st) {
+  const bool is16 = precision >= RESEP_PREC_BF16;   // 2: the handle's bf16 weight mode; test-only codes 3: bf16(W) only, 4: hi+lo
+  const size_t esz = is16 ? 2 : 4;
+  void *a2 = nullptr, *w2 = nullptr, *w3 = nullptr;
+  RESEP_CUDA(h, cudaMalloc(&a2, (size_t)M * K * esz));
+  RESEP_CUDA(h, cudaMalloc(&w2, (size_t)N * K * esz));
+  RESEP_CUDA(h, cudaMalloc(&w3, (size_t)N * K * esz));
+  int rc;
+  if (is16) {
+    k_convert<bf16><<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, (bf16*)a2, M * K);
+    k_split_w16<<<(unsigned)(((int64_t)N * K + 255) / 256), 256, 0, st>>>(W, (bf16*)w2, (bf16*)w3, (int64_t)N * K);
+    h->launches += 2;
+    rc = gemm_bf16<EPI_STORE_F32>(h, precision == 2 ? h->w16_mode : precision - 3, (bf16*)a2, (bf16*)w2, (bf16*)w3, bias, out, M, N, K,
+                                  relu, st);
+  } else {
+    k_convert<float><<<(unsigned)((M * K + 255) / 256), 256, 0, st>>>(A, (float*)a2, M * K);
+    k_split_tf32<<<(unsigned)(((int64_t)N * K + 255) / 256), 256, 0, st>>>(W, (float*)w2, (float*)w3, (int64_t)N * K);
+    h->launches += 2;
+    rc = launch_gemm_tc<float, EPI_STORE_F32, true>(h, (float*)a2, (float*)w2, bias, out, M, N, K, relu, st, (float*)w3);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(a2);
+  cudaFree(w2);
+  cudaFree(w3);
+  if (rc) return rc;
+  if (e != cudaSuccess) return set_err(h, RESEP_ECUDA, std::string("tc_linear_test: ") + cudaGetErrorString(e));
+  return RESEP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One transformer layer with tensor-core GEMMs.
+//   bf16 mode: y / qkv / ctx / hid are bf16 (half the bytes of the fp32 scratch regions they live in)
+//   tf32 mode: fp32 buffers holding tf32-rounded values; attention uses the fp32 kernel
+int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
+                 const int* tile_seq, const int* tile_q0, int n_tiles, float* y, float* qkv, float* ctx, float* hid,
+                 int precision, cudaStream_t st) {
+  int rc;
+  if (precision == RESEP_PREC_BF16) {
+    bf16 *yb = reinterpret_cast<bf16*>(y), *qb = reinterpret_cast<bf16*>(qkv), *cb = reinterpret_cast<bf16*>(ctx),
+         *hb = reinterpret_cast<bf16*>(hid);
+    if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
+    if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
+    if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st))) return rc;
+    if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;
+    if ((rc = launch_layernorm<bf16>(h, o, lw.norm2_w, lw.norm2_b, yb, rows, st))) return rc;
+    if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.f1_w_bf, lw.f1_w_bl, lw.f1_b, hb, rows, FFN, D, true, st))) return rc;
+    if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, hb, lw.f2_w_bf, lw.f2_w_bl, lw.f2_b, o, rows, D, FFN, false, st))) return rc;
+    return RESEP_OK;
+  }
+  // tf32: operands are fp32 in memory; the tensor core reads the top 19 bits, so every producer rounds
+  // to tf32 (cvt.rna) first and the weights were rounded on upload.
+  if ((rc = launch_layernorm_tf32(h, o, lw.norm1_w, lw.norm1_b, y, rows, st))) return rc;
+  if ((rc = launch_gemm_tc<float, EPI_STORE_F32, true>(h, y, lw.in_w_tf, lw.in_b, qkv, rows, 3 * D, D, false, st, lw.in_w_lo))) return rc;
+  if ((rc = launch_attention_f32(h, qkv, ctx, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st))) return rc;
+  if ((rc = launch_round_tf32(h, ctx, rows * D, st))) return rc;
+  if ((rc = launch_gemm_tc<float, EPI_RESID_F32, true>(h, ctx, lw.out_w_tf, lw.out_b, o, rows, D, D, false, st, lw.out_w_lo))) return rc;
+  if ((rc = launch_layernorm_tf32(h, o, lw.norm2_w, lw.norm2_b, y, rows, st))) return rc;
+  if ((rc = launch_gemm_tc<float, EPI_STORE_TF32, true>(h, y, lw.f1_w_tf, lw.f1_b, hid, rows, FFN, D, true, st, lw.f1_w_lo))) return rc;
+  if ((rc = launch_gemm_tc<float, EPI_RESID_F32, true>(h, hid, lw.f2_w_tf, lw.f2_b, o, rows, D, FFN, false, st, lw.f2_w_lo))) return rc;
+  return RESEP_OK;
+}
+
+int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, int64_t M, int precision,
+                cudaStream_t st) {
+  int rc;
+  if (precision == RESEP_PREC_BF16) {
+    bf16* yb = reinterpret_cast<bf16*>(y_scratch);
+    if ((rc = launch_prelu_t<bf16>(h, a, h->w.prelu_a, yb, M * D, st))) return rc;
+    return gemm_bf16<EPI_STORE_F32>(h, h->w16_mode, yb, h->w.fc_w_bf, h->w.fc_w_bl, h->w.fc_b, mask, M, NSPK * D, D,
+                                   true, st);
+  }
+  if ((rc = launch_prelu(h, a, h->w.prelu_a, y_scratch, M * D, st))) return rc;
+  if ((rc = launch_round_tf32(h, y_scratch, M * D, st))) return rc;
+  return launch_gemm_tc<float, EPI_STORE_F32, true>(h, y_scratch, h->w.fc_w_tf, h->w.fc_b, mask, M, NSPK * D, D, true, st,
+                                                  h->w.fc_w_lo);
+}
+
+}  // namespace resep

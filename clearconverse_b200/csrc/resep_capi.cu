@@ -3,6 +3,7 @@
 // SepformerSeparation.separate_batch (speechbrain/inference/separation.py), called by the
 // reference at /root/reference/back/api.py:1077.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -30,6 +31,33 @@ struct ArenaBuilder {
     return off;
   }
   size_t add_f32(const float* src, size_t n) { return add(src, n * sizeof(float)); }
+  size_t add_tf32(const float* src, size_t n) {   // round to nearest, ties away (== cvt.rna.tf32.f32)
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t u;
+      std::memcpy(&u, &src[i], 4);
+      if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+      std::memcpy(&tmp[i], &u, 4);
+    }
+    return add(tmp.data(), n * sizeof(float));
+  }
+  static float tf32_rna(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+  }
+  size_t add_tf32_lo(const float* src, size_t n) {   // tf32(W - tf32(W)): second term of the split weights
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = tf32_rna(src[i] - tf32_rna(src[i]));
+    return add(tmp.data(), n * sizeof(float));
+  }
+  size_t add_bf16_lo(const float* src, size_t n) {
+    std::vector<bf16> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i] - __bfloat162float(__float2bfloat16_rn(src[i])));
+    return add(tmp.data(), n * sizeof(bf16));
+  }
   size_t add_bf16(const float* src, size_t n) {
     std::vector<bf16> tmp(n);
     for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
@@ -48,8 +76,13 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   auto F = [&](const float*& slot, const float* src, size_t n) {
     fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_f32(src, n)});
   };
-  auto Bf = [&](const bf16*& slot, const float* src, size_t n) {
+  auto Bf = [&](const bf16*& slot, const bf16*& slot_lo, const float* src, size_t n) {
     fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_bf16(src, n)});
+    fixes.push_back({reinterpret_cast<const void**>(&slot_lo), ab.add_bf16_lo(src, n)});
+  };
+  auto Tf = [&](const float*& slot, const float*& slot_lo, const float* src, size_t n) {
+    fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_tf32(src, n)});
+    fixes.push_back({reinterpret_cast<const void**>(&slot_lo), ab.add_tf32_lo(src, n)});
   };
   F(d.enc_w, w->enc_w, D * KSZ);
   F(d.dec_w, w->dec_w, D * KSZ);
@@ -57,7 +90,8 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   F(d.fc_w, w->fc_w, NSPK * D * D);
   F(d.fc_b, w->fc_b, NSPK * D);
   F(d.pe, w->pe, (size_t)w->pe_rows * D);
-  Bf(d.fc_w_bf, w->fc_w, NSPK * D * D);
+  Bf(d.fc_w_bf, d.fc_w_bl, w->fc_w, NSPK * D * D);
+  Tf(d.fc_w_tf, d.fc_w_lo, w->fc_w, NSPK * D * D);
   d.pe_rows = w->pe_rows;
   const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
   for (int b = 0; b < 3; ++b) {
@@ -78,10 +112,14 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
       F(t.norm2_w, s.norm2_w, D); F(t.norm2_b, s.norm2_b, D);
       F(t.f1_w, s.ffn1_w, (size_t)FFN * D); F(t.f1_b, s.ffn1_b, FFN);
       F(t.f2_w, s.ffn2_w, (size_t)D * FFN); F(t.f2_b, s.ffn2_b, D);
-      Bf(t.in_w_bf, s.in_proj_w, 3 * D * D);
-      Bf(t.out_w_bf, s.out_proj_w, D * D);
-      Bf(t.f1_w_bf, s.ffn1_w, (size_t)FFN * D);
-      Bf(t.f2_w_bf, s.ffn2_w, (size_t)D * FFN);
+      Bf(t.in_w_bf, t.in_w_bl, s.in_proj_w, 3 * D * D);
+      Bf(t.out_w_bf, t.out_w_bl, s.out_proj_w, D * D);
+      Bf(t.f1_w_bf, t.f1_w_bl, s.ffn1_w, (size_t)FFN * D);
+      Bf(t.f2_w_bf, t.f2_w_bl, s.ffn2_w, (size_t)D * FFN);
+      Tf(t.in_w_tf, t.in_w_lo, s.in_proj_w, 3 * D * D);
+      Tf(t.out_w_tf, t.out_w_lo, s.out_proj_w, D * D);
+      Tf(t.f1_w_tf, t.f1_w_lo, s.ffn1_w, (size_t)FFN * D);
+      Tf(t.f2_w_tf, t.f2_w_lo, s.ffn2_w, (size_t)D * FFN);
     }
   }
   if (h->arena == nullptr || h->arena_bytes < ab.host.size()) {
@@ -372,6 +410,10 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
   if (!h) return set_err(nullptr, RESEP_EINVAL, "out of host memory");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* m = getenv("RESEP_W16")) {   // weight operand of the bf16 mode (see DESIGN.md "precision modes")
+    if (!strcmp(m, "bf16")) h->w16_mode = 0;          // single rounded bf16 weight: fails the SI-SNR gate
+    else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;
+  }
   int rc = upload_weights(h, w);
   if (rc) {
     g_create_err = h->err;

@@ -29,7 +29,10 @@ typedef __nv_bfloat16 bf16;
 
 struct LayerDev {
   const float *norm1_w, *norm1_b, *in_w, *in_b, *out_w, *out_b, *norm2_w, *norm2_b, *f1_w, *f1_b, *f2_w, *f2_b;
-  const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;
+  const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;       // bf16 copies (RESEP_PREC_BF16)
+  const bf16 *in_w_bl, *out_w_bl, *f1_w_bl, *f2_w_bl;       // bf16(W - bf16(W)): low part for the split-weight mode
+  const float *in_w_tf, *out_w_tf, *f1_w_tf, *f2_w_tf;      // tf32-rounded fp32 copies (RESEP_PREC_TF32): hi part
+  const float *in_w_lo, *out_w_lo, *f1_w_lo, *f2_w_lo;      // tf32(W - hi): the TF32 mode runs W = hi + lo
 };
 struct BlockDev {
   LayerDev layers[NL];
@@ -37,7 +40,8 @@ struct BlockDev {
 };
 struct WeightsDev {
   const float *enc_w, *dec_w, *prelu_a, *fc_w, *fc_b, *pe;
-  const bf16* fc_w_bf;
+  const bf16 *fc_w_bf, *fc_w_bl;
+  const float *fc_w_tf, *fc_w_lo;
   int64_t pe_rows;
   BlockDev blk[3];  // 0 = seg_model[0], 1 = seg_model[1], 2 = mem_model[0]
 };
@@ -82,6 +86,7 @@ struct ResepHandle {
   std::vector<resep::Plan*> plans;
   uint64_t tick = 0;
   int64_t launches = 0;
+  int w16_mode = 1;       // RESEP_PREC_BF16 weight operand: 1 = bf16 hi + lo (two MMAs per K-slice), 0 = bf16(W) only
   bool tc_ready = false;  // tensor maps for the tcgen05 path built
   void* tc_state = nullptr;
 };
@@ -123,6 +128,10 @@ int launch_attention_f32(ResepHandle* h, const float* qkv, float* ctx, int n_seq
 int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const float* fn_b, const float* gln_w,
                           const float* gln_b, const float* xin, float* out, float* seq_mean, int n_seq, int seq_len,
                           const int* seq_off, cudaStream_t st);
+// y = round_to_tf32(LayerNorm(x)); x[i] = round_to_tf32(x[i]) in place
+int launch_layernorm_tf32(ResepHandle* h, const float* x, const float* w, const float* b, float* y, int64_t rows,
+                          cudaStream_t st);
+int launch_round_tf32(ResepHandle* h, float* x, int64_t n, cudaStream_t st);
 int launch_prelu(ResepHandle* h, const float* x, const float* a, float* y, int64_t n, cudaStream_t st);
 template <typename OutT>
 int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st);

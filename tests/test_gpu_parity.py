@@ -1,10 +1,9 @@
 """GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the drop-in
 Python surface and the C ABI, against the CPU oracle and the committed golden vectors.
 
-Tolerances (BASELINE.json north_star): fp32 waveforms max-abs <= 1e-3 (the fp32 and tf32
-modes); the bf16 mode is held to an SI-SNR delta <= 0.05 dB, where "SI-SNR delta" is defined
-here as |SI-SNR(est_bf16, src) - SI-SNR(est_oracle, src)| with src = the oracle's own fp32
-estimate shifted... -- see ``si_snr_delta`` below for the exact, well-conditioned definition.
+Tolerances (BASELINE.json north_star): max-abs <= 1e-3 on fp32 waveforms for the fp32-tolerance
+modes ("fp32" FMA kernels and "tf32" tcgen05 kernels); SI-SNR delta <= 0.05 dB for the bf16
+mode, with "SI-SNR delta" defined in ``si_snr_delta`` below.
 """
 import ctypes as C
 import glob
@@ -203,7 +202,7 @@ def test_tc_linear_matches_fp32_kernel(sep_fp32):
         W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         b = torch.randn(N, generator=g).cuda()
         outs = {}
-        for prec in (0, 1, 2):
+        for prec in (0, 1, 2, 3, 4):
             o = torch.empty(M, N, device="cuda")
             rc = eng.lib.resep_linear_fwd(eng.handle, A.data_ptr(), W.data_ptr(), b.data_ptr(), o.data_ptr(), M, N, K,
                                           relu, prec, st)
@@ -214,7 +213,9 @@ def test_tc_linear_matches_fp32_kernel(sep_fp32):
             ref = ref.clamp_min(0)
         assert (outs[0].double() - ref).abs().max().item() < 1e-4
         assert (outs[1].double() - ref).abs().max().item() < 5e-3, (M, N, K)     # tf32 operands
-        assert (outs[2].double() - ref).abs().max().item() < 5e-2, (M, N, K)     # bf16 operands
+        assert (outs[2].double() - ref).abs().max().item() < 3e-2, (M, N, K)     # bf16 activations, W = hi + lo
+        assert (outs[3].double() - ref).abs().max().item() < 8e-2, (M, N, K)     # test code 3: bf16(W) only
+        assert torch.equal(outs[2], outs[4])                                       # test code 4 == the default mode
 
 
 @pytest.mark.parametrize("B,T,seed", [(1, 100, 5), (2, 2000, 2), (1, 32000, 1), (3, 9000, 5)])
