@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the RE-SepFormer overlap-separation path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json
+configs[1], 16 x 4 s synthetic 8 kHz two-speaker mixtures through ``separate_batch`` in the
+bf16 mode on one B200.  With N > 1 every rank runs that same per-GPU batch (independent
+segments shard with no data-path collective -> weak scaling) and ``value`` is the whole-job
+audio-seconds per second with the step time taken as the max over ranks.
+
+Prints ONE JSON line (rank 0).  ``value`` is measured with the inputs resident in HBM; ``e2e``
+goes through the public Python API with pinned HOST buffers, H2D and D2H inside the timed
+region.  ``roofline`` is the dominant kernel of the step (CUDA-event timing per kernel on the
+launch stream, taken in a separate pass); ``cpu_baseline`` is the oracle (the only runnable
+form of the reference's CPU path: speechbrain is not installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "separated_audio_seconds_per_second"
+UNIT = "audio-s/s"
+SAMPLE_RATE = 8000
+BATCH, SECONDS = 16, 4
+T = SECONDS * SAMPLE_RATE
+WORKLOAD = "resepformer-wsj02mix random-init, batch 16 x 4 s synthetic 8 kHz 2-speaker mixtures (BASELINE configs[1])"
+
+
+def peaks():
+    fb = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        d["_src"] = "measured"
+        return d
+    except Exception:
+        return fb
+
+
+# ------------------------------------------------------------------------------------- model shapes
+def shapes(batch, t, coupled=True):
+    L = (t - 16) // 8 + 1
+    S = L // 150 + 1
+    chunks = batch * S
+    M = chunks * 150
+    mem_seqs = [chunks] if coupled else [S] * batch
+    return L, S, chunks, M, mem_seqs
+
+
+def kernel_work(name: str, batch: int, t: int):
+    """(bound, algorithmic FLOPs or bytes summed over ALL launches of this kernel in one step).
+    Per-unit figures are SURVEY.md section 8(d): multiply-add = 2 FLOPs; per token-layer QKV 98,304,
+    attention 76,800, out-proj 32,768, FFN 524,288."""
+    L, S, chunks, M, mem_seqs = shapes(batch, t)
+    rows = 16 * M + 8 * chunks                         # token-layers: 16 intra layers + 8 memory layers
+    att = 16 * chunks * 8 * 4 * 150 * 150 * 16 + 8 * sum(4 * n * n * 128 for n in mem_seqs)
+    if name.startswith("k_gemm_tc<bf16,bf16"):        # QKV + FFN1
+        return "tensor", rows * (98_304 + 262_144)
+    if name.startswith("k_gemm_tc<bf16,resid"):       # out-proj + FFN2
+        return "tensor", rows * (32_768 + 262_144)
+    if name.startswith("k_gemm_tc<bf16,f32"):         # output_fc
+        return "tensor", M * 65_536
+    if name.startswith("k_layer_tc"):                  # fused layer kernel: every GEMM of the layer
+        return "tensor", rows * 655_360
+    if name.startswith("k_attention"):
+        return "tensor", att
+    if name.startswith("k_layernorm"):
+        return "hbm", 2 * rows * (512 + 256)
+    if name.startswith("k_block_epilogue"):
+        return "hbm", (2 * M + chunks) * 128 * 4 * 4
+    if name.startswith("k_decoder"):
+        return "hbm", batch * L * (256 + 128) * 4 + batch * t * 8
+    if name.startswith("k_encoder"):
+        return "hbm", batch * t * 4 + M * 512
+    return None, None
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(1.0)
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def make_oracle(sds):
+    import torch
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    m = OracleSepformerSeparation(seed=None, distinct_blocks=False)
+    for k in ("encoder", "masknet", "decoder"):
+        m.mods[k].load_state_dict(sds[k])
+    return m
+
+
+def time_oracle(sds, items: int, reps: int, warmup: int = 1):
+    """Oracle (fp32 eager PyTorch, all host threads) on `items` of the 16 mixtures per repetition."""
+    import torch
+    from clearconverse_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = make_oracle(sds)
+    mix = synth.synth_batch(items, T, seed=2)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        m.separate_batch(mix)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return items * SECONDS / statistics.median(times), times, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  speechbrain cannot be
+    installed here, so this is the oracle port on the host cores; rank 0 alone runs it."""
+    if rank != 0:
+        return
+    from clearconverse_b200 import weights
+    sds = weights.random_init_state_dicts(0)
+    items = 2
+    import torch
+    from clearconverse_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = make_oracle(sds)
+    mix = synth.synth_batch(items, T, seed=2)
+    for _ in range(max(1, min(args.warmup, 3))):
+        m.separate_batch(mix)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.separate_batch(mix)
+    dt = time.perf_counter() - t0
+    value = args.steps * items * SECONDS / dt
+    sample = f"{items} of the {BATCH} mixtures (B={items} x {SECONDS} s) per step, oracle fp32 eager, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": BATCH, "seconds_per_item": SECONDS, "sample_rate": SAMPLE_RATE},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from clearconverse_b200 import SepformerSeparation, synth, weights
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    sds = weights.random_init_state_dicts(0)
+    sep = SepformerSeparation(sds, device=dev, precision=args.precision, batch_mode="coupled")
+    host_mix = synth.synth_batch(BATCH, T, seed=2 + rank).pin_memory()
+    mix = host_mix.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: K steps, each bracketed by events, L2 flushed in between
+    for _ in range(args.warmup):
+        sep.separate_batch(mix)
+    barrier()
+    l0 = sep.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            sep.separate_batch(mix)
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = sep.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = total_ms.item() / 1e3
+    audio_s = world * BATCH * SECONDS * args.steps
+    value = audio_s / total_s
+
+    # ---------------- end to end: pinned host in, pinned host out, through the public API
+    host_out = torch.empty(BATCH, T, 2, dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        host_out.copy_(sep.separate_batch(host_mix), non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        est = sep.separate_batch(host_mix)                 # H2D of the step's input inside
+        host_out.copy_(est, non_blocking=True)             # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = audio_s / e2e_s.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (separate pass; events around every launch)
+    pk = peaks()
+    reps = 5
+    prof = sep.profile_kernels(lambda: [sep.separate_batch(mix) for _ in range(reps)])
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    roofline = None
+    if top[0]:
+        name, rec = top
+        bound, work = kernel_work(name, BATCH, T)
+        avg_ms = rec["ms"] / rec["launches"]
+        if bound == "tensor":
+            peak, unit = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "TFLOP/s"
+            achieved = work * reps / rec["launches"] / (avg_ms / 1e3) / 1e12
+        elif bound == "hbm":
+            peak, unit = pk["hbm_gbs"], "GB/s"
+            achieved = work * reps / rec["launches"] / (avg_ms / 1e3) / 1e9
+        else:
+            peak = unit = achieved = None
+        roofline = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "peak_source": pk["_src"] + (" (sustained bf16: kernel timed inside the step)" if bound == "tensor" else ""),
+                    "avg_launch_us": 1e3 * avg_ms, "launches_per_step": rec["launches"] / reps,
+                    "share_of_step": rec["ms"] / sum(r["ms"] for r in prof.values()),
+                    "kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---------------- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, times, threads = time_oracle(sds, items=4, reps=5)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"4 of the {BATCH} mixtures (B=4 x {SECONDS} s), oracle fp32 eager PyTorch, 1 warm-up + median of 5 "
+                         f"({sum(times):.1f} s of CPU work)", "host_cpus": os.cpu_count()}
+
+    flops_step = None
+    from clearconverse_b200.sharding import flops_of
+    L, S, chunks, M, mem_seqs = shapes(BATCH, T)
+    flops_step = BATCH * flops_of(T, mem_seq_len=chunks)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms.item() / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "seconds_per_item": SECONDS, "sample_rate": SAMPLE_RATE,
+                   "batch_mode": "coupled", "weights": "random-init (seed 0), bf16 hi+lo operands, fp32 accumulate",
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "parallelism": f"replicated x{world}, no collective"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * T * 4, "d2h_bytes_per_step": BATCH * T * 2 * 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "algorithmic_tflops_per_s": flops_step * args.steps * world / total_s / 1e12,
+        "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

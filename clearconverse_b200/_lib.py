@@ -60,6 +60,8 @@ SYMBOLS = {
     "resep_forward_debug": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_int, C.c_int, C.c_void_p, C.POINTER(ResepDebugOut)]),
     "resep_launch_count": (C.c_int64, [_H]),
+    "resep_profile": (C.c_int, [_H, C.c_int]),
+    "resep_profile_report": (C.c_int, [_H, C.c_char_p, C.c_size_t]),
     "resep_encoder_fwd": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "resep_layer_fwd": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p]),

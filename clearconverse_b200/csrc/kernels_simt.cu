@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(D) k_encoder_chunked(const float* __restrict__
 }
 
 int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st) {
+  ProfScope prof_scope_69(h, "k_encoder_chunked", st);
   k_encoder_chunked<<<(unsigned)(p.n_chunks * (CHUNK / ENC_ROWS)), D, 0, st>>>(
       mix, h->w.enc_w, p.d_item_off, p.d_item_len, p.d_item_L, p.d_chunk_item, p.d_chunk_frame0, x0);
   RESEP_LAUNCH_CHECK(h, "k_encoder_chunked");
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(D) k_encoder_single(const float* __restrict__ 
 
 int launch_encoder_single(ResepHandle* h, const float* mix, int64_t T, float* tokens, cudaStream_t st) {
   int L = (int)((T - KSZ) / STRIDE + 1);
+  ProfScope prof_scope_98(h, "k_encoder_single", st);
   k_encoder_single<<<(L + ENC_ROWS - 1) / ENC_ROWS, D, 0, st>>>(mix, h->w.enc_w, T, L, tokens);
   RESEP_LAUNCH_CHECK(h, "k_encoder_single");
   return RESEP_OK;
@@ -126,6 +128,7 @@ int launch_block_prologue(ResepHandle* h, const float* xprev, const float* hc, f
                           const int* pos, int seq_len, cudaStream_t st) {
   int64_t n4 = rows * (D / 4);
   if (n4 == 0) return RESEP_OK;
+  ProfScope prof_scope_128(h, "k_block_prologue", st);
   k_block_prologue<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(xprev, hc, xin, o, n4, h->w.pe, pos, seq_len);
   RESEP_LAUNCH_CHECK(h, "k_block_prologue");
   return RESEP_OK;
@@ -175,6 +178,7 @@ template <typename OutT>
 int launch_layernorm(ResepHandle* h, const float* x, const float* w, const float* b, OutT* y, int64_t rows,
                      cudaStream_t st) {
   if (rows == 0) return RESEP_OK;
+  ProfScope prof_scope_177(h, "k_layernorm", st);
   k_layernorm<OutT><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, b, y, rows);
   RESEP_LAUNCH_CHECK(h, "k_layernorm");
   return RESEP_OK;
@@ -195,6 +199,7 @@ __global__ void k_round_tf32(float* x, int64_t n4) {
 int launch_round_tf32(ResepHandle* h, float* x, int64_t n, cudaStream_t st) {
   const int64_t n4 = n / 4;
   if (n4 == 0) return RESEP_OK;
+  ProfScope prof_scope_197(h, "k_round_tf32", st);
   k_round_tf32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, n4);
   RESEP_LAUNCH_CHECK(h, "k_round_tf32");
   return RESEP_OK;
@@ -263,6 +268,7 @@ int launch_gemm_f32(ResepHandle* h, const float* A, const float* W, const float*
   if (M == 0) return RESEP_OK;
   if (N % GB != 0 || K % GK != 0) return set_err(h, RESEP_EINVAL, "gemm_f32: N % 64 or K % 16 != 0");
   dim3 grid((unsigned)((M + GB - 1) / GB), (unsigned)(N / GB));
+  ProfScope prof_scope_265(h, "k_gemm_f32", st);
   k_gemm_f32<<<grid, 256, 0, st>>>(A, W, bias, residual, C, M, N, K, relu ? 1 : 0);
   RESEP_LAUNCH_CHECK(h, "k_gemm_f32");
   return RESEP_OK;
@@ -355,6 +361,7 @@ __global__ void __launch_bounds__(QT) k_attention_f32(const float* __restrict__ 
 
 int launch_attention_f32(ResepHandle* h, const float* qkv, float* ctx, int n_seq, int seq_len, const int* seq_off,
                          const int* tile_seq, const int* tile_q0, int n_tiles, cudaStream_t st) {
+  ProfScope prof_scope(h, "k_attention_f32", st);
   if (tile_seq == nullptr) {
     if (n_seq == 0) return RESEP_OK;
     if (seq_len <= 160) {
@@ -449,6 +456,7 @@ int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const flo
                           const float* gln_b, const float* xin, float* out, float* seq_mean, int n_seq, int seq_len,
                           const int* seq_off, cudaStream_t st) {
   if (n_seq == 0) return RESEP_OK;
+  ProfScope prof_scope_451(h, "k_block_epilogue", st);
   k_block_epilogue<<<(unsigned)n_seq, 256, 0, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, seq_off);
   RESEP_LAUNCH_CHECK(h, "k_block_epilogue");
   return RESEP_OK;
@@ -473,6 +481,7 @@ template <typename OutT>
 int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st) {
   int64_t n4 = n / 4;
   if (n4 == 0) return RESEP_OK;
+  ProfScope prof_scope_475(h, "k_prelu", st);
   k_prelu<OutT><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, a, y, n4);
   RESEP_LAUNCH_CHECK(h, "k_prelu");
   return RESEP_OK;
@@ -545,6 +554,7 @@ int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Pla
   if (p.n_dec_tiles == 0) return RESEP_OK;
   const size_t smem = ((DEC_SLOTS + 1) * NSPK * D + D * KSZ + (DEC_SLOTS + 1) * NSPK * KSZ) * sizeof(float);
   static_assert(((DEC_SLOTS + 1) * NSPK * D + D * KSZ + (DEC_SLOTS + 1) * NSPK * KSZ) * sizeof(float) <= 48 * 1024, "decoder smem");
+  ProfScope prof_scope_547(h, "k_decoder", st);
   k_decoder<<<(unsigned)p.n_dec_tiles, 256, smem, st>>>(mask, x0, h->w.dec_w, p.d_item_off, p.d_item_len, p.d_item_L,
                                                        p.d_item_row0, p.d_dec_tile_item, p.d_dec_tile_slot0, est);
   RESEP_LAUNCH_CHECK(h, "k_decoder");

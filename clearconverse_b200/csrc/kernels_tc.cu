@@ -262,6 +262,10 @@ static int launch_gemm_tc(ResepHandle* h, const TIn* A, const TIn* W, const floa
   RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  static const char* const kEpiName[4] = {"f32", "bf16", "resid", "tf32"};
+  static const std::string kname = std::string("k_gemm_tc<") + (sizeof(TIn) == 2 ? "bf16" : "tf32") + "," + kEpiName[EPI] +
+                                   (SPLITW ? ",hi+lo>" : ">");
+  ProfScope prof_scope(h, kname.c_str(), st);
   kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, tmWlo, bias, out, M, N, K, relu ? 1 : 0);
   RESEP_LAUNCH_CHECK(h, "k_gemm_tc");
   return RESEP_OK;
@@ -437,6 +441,7 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
                                  const int* tile_seq, const int* tile_q0, int n_tiles128, cudaStream_t st) {
+  ProfScope prof_scope(h, "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
   // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
   // of the next tile with identical results).

@@ -4,6 +4,7 @@
 // reference at /root/reference/back/api.py:1077.
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -440,6 +441,7 @@ int resep_destroy(ResepHandle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   tc_destroy(h);
+  resep_profile(h, 0);
   for (Plan* p : h->plans) free_plan(p);
   if (h->arena) cudaFree(h->arena);
   delete h;
@@ -449,6 +451,42 @@ int resep_destroy(ResepHandle* h) {
 const char* resep_last_error(const ResepHandle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int64_t resep_launch_count(const ResepHandle* h) { return h ? h->launches : 0; }
+
+int resep_profile(ResepHandle* h, int enable) {
+  if (!h) return RESEP_EINVAL;
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  h->prof_on = enable != 0;
+  return RESEP_OK;
+}
+
+int resep_profile_report(ResepHandle* h, char* buf, size_t cap) {
+  if (!h) return RESEP_EINVAL;
+  if (!buf || cap < 3) return set_err(h, RESEP_EINVAL, "buffer too small");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  RESEP_CUDA(h, cudaDeviceSynchronize());
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<long long> cnt;
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = 0.f;
+    size_t i = 0;
+    for (; i < names.size(); ++i) if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[i] += t;
+    cnt[i] += 1;
+  }
+  std::string js = "{";
+  for (size_t i = 0; i < names.size(); ++i) {
+    char tmp[256];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", i ? ", " : "", names[i].c_str(), ms[i], cnt[i]);
+    js += tmp;
+  }
+  js += "}";
+  snprintf(buf, cap, "%s", js.c_str());
+  return resep_profile(h, 0);
+}
 
 int resep_workspace_bytes(ResepHandle* h, int B, const int64_t* item_len, int precision, size_t* bytes) {
   if (!h) return RESEP_EINVAL;

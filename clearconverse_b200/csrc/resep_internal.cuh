@@ -87,6 +87,9 @@ struct ResepHandle {
   uint64_t tick = 0;
   int64_t launches = 0;
   int w16_mode = 1;       // RESEP_PREC_BF16 weight operand: 1 = bf16 hi + lo (two MMAs per K-slice), 0 = bf16(W) only
+  bool prof_on = false;   // resep_profile(): bracket every launch with CUDA events
+  struct ProfRec { cudaEvent_t a, b; const char* name; };
+  std::vector<ProfRec> prof;
   bool tc_ready = false;  // tensor maps for the tcgen05 path built
   void* tc_state = nullptr;
 };
@@ -101,6 +104,23 @@ int set_err(ResepHandle* h, int code, const std::string& msg);
     if (e__ != cudaSuccess)                                                                    \
       return ::resep::set_err(h, RESEP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
+// RAII: in profiling mode records an event before and after the launch(es) issued during its lifetime.
+struct ProfScope {
+  ResepHandle* h;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(ResepHandle* h_, const char* name, cudaStream_t st_) : h(h_), st(st_) {
+    if (!h->prof_on) return;
+    ResepHandle::ProfRec r{nullptr, nullptr, name};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    h->prof.push_back(r);
+    idx = (int)h->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof[idx].b, st);
+  }
+};
 #define RESEP_LAUNCH_CHECK(h, name)                                                            \
   do {                                                                                         \
     (h)->launches++;                                                                           \

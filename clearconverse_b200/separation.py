@@ -323,5 +323,18 @@ class SepformerSeparation:
     def launch_count(self) -> int:
         return self._engine.launch_count()
 
+    def profile_kernels(self, fn) -> dict:
+        """Run ``fn()`` with every kernel launch bracketed by CUDA events on its stream and
+        return {kernel name: {"ms": total, "launches": n}} (bench.py's roofline source)."""
+        import json
+        eng = self._engine
+        _lib.check(eng.lib, eng.handle, eng.lib.resep_profile(eng.handle, 1))
+        try:
+            fn()
+        finally:
+            buf = C.create_string_buffer(1 << 16)
+            _lib.check(eng.lib, eng.handle, eng.lib.resep_profile_report(eng.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def close(self):
         self._engine.close()

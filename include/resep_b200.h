@@ -150,6 +150,14 @@ int resep_forward_debug(ResepHandle* h, const float* mix, const int64_t* item_of
 /* Kernels launched by this handle since creation (bench.py's "gpu_launches" evidence). */
 int64_t resep_launch_count(const ResepHandle* h);
 
+/* Per-kernel device timing for bench.py's roofline object: resep_profile(h,1) makes every kernel
+ * launch of this handle be bracketed by CUDA events on its launch stream; resep_profile_report
+ * synchronises, sums the event durations per kernel name, writes a JSON object
+ * {"kernel": {"ms": total_ms, "launches": n}, ...} into buf (NUL-terminated, truncated to cap)
+ * and switches profiling off.  Not for use inside a timed region (event records perturb it). */
+int resep_profile(ResepHandle* h, int enable);
+int resep_profile_report(ResepHandle* h, char* buf, size_t cap);
+
 /* ---- per-kernel entry points (unit parity tests; DEVICE pointers, stream-ordered) ------- */
 
 /* dual_path.Encoder: relu(conv1d k16 s8) of ONE item -> token-major [L,128]. */
