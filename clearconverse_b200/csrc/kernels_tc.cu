@@ -12,26 +12,15 @@
 //   y = LN1(x); x += OutProj(MHA(y)); y = LN2(x); x += W2 relu(W1 y + b1) + b2
 #include <cuda.h>
 
-#include <map>
-#include <mutex>
+#include <cstdlib>
 
-#include "ptx_sm100.cuh"
-#include "resep_tc.cuh"
+#include "tc_common.cuh"
 
 namespace resep {
 
 using namespace ptx;
 
-// ------------------------------------------------------------------------------------------------
-// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled g_encode = nullptr;
-
-struct TcState {
-  int dummy = 0;
-};
+PFN_encodeTiled g_encode = nullptr;
 
 int tc_init(ResepHandle* h) {
   if (h->tc_ready) return RESEP_OK;
@@ -48,21 +37,6 @@ int tc_init(ResepHandle* h) {
 }
 
 void tc_destroy(ResepHandle* h) { h->tc_ready = false; }
-
-// 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes of columns], 128B swizzle, OOB -> 0.
-template <typename T>
-static int make_tmap(ResepHandle* h, CUtensorMap* m, const T* base, int64_t rows, int cols, int box_rows) {
-  const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(T)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, dt, 2, const_cast<T*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-  return RESEP_OK;
-}
 
 // ------------------------------------------------------------------------------------------------
 // GEMM
@@ -94,8 +68,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr uint32_t FMT = sizeof(TIn) == 2 ? UMMA_BF16 : UMMA_TF32;
   constexpr uint32_t IDESC = umma_idesc(FMT, FMT, BM, BN);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;                          // [STAGES]
   uint64_t* empty_bar = bars + STAGES;                // [STAGES]
@@ -527,6 +500,8 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
     if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
     if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
     if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st))) return rc;
+    static const bool fused = !(getenv("RESEP_FUSED") && getenv("RESEP_FUSED")[0] == '0');
+    if (fused) return launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
     if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;
     if ((rc = launch_layernorm<bf16>(h, o, lw.norm2_w, lw.norm2_b, yb, rows, st))) return rc;
     if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.f1_w_bf, lw.f1_w_bl, lw.f1_b, hb, rows, FFN, D, true, st))) return rc;

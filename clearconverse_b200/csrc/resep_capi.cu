@@ -452,6 +452,13 @@ const char* resep_last_error(const ResepHandle* h) { return h ? h->err.c_str() :
 
 int64_t resep_launch_count(const ResepHandle* h) { return h ? h->launches : 0; }
 
+// development aid (not in the public header): copy the k_post_tc clock trace of CTA 0 to `out[128]`
+extern "C" int resep_debug_trace(long long* out) {
+  if (!resep::g_post_trace) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, resep::g_post_trace, 256 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+
 int resep_profile(ResepHandle* h, int enable) {
   if (!h) return RESEP_EINVAL;
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -10,6 +10,12 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
                  const int* tile_seq, const int* tile_q0, int n_tiles, float* y, float* qkv, float* ctx, float* hid,
                  int precision, cudaStream_t st);
 
+// Fused post-attention half of a layer (kernels_layer.cu), bf16 mode:
+//   o <- o' + W2 relu(W1 LN2(o') + b1) + b2,  o' = o + ctx . Wo^T + bo      (o fp32 in place, ctx bf16)
+int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st);
+
+extern long long* g_post_trace;   // development aid: clock trace buffer of k_post_tc (null unless RESEP_TRACE is set)
+
 // output_fc: mask[M,256] = relu(prelu(a) . fc_w^T + fc_b)   (fp32 out)
 int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, int64_t M, int precision, cudaStream_t st);
 

@@ -1,0 +1,33 @@
+// Shared by the tensor-core translation units: PTX wrappers + TMA tensor-map construction.
+#pragma once
+#include <cuda.h>
+
+#include <string>
+
+#include "ptx_sm100.cuh"
+#include "resep_tc.cuh"
+
+namespace resep {
+
+// driver entry point for cuTensorMapEncodeTiled (resolved at run time: no link dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+extern PFN_encodeTiled g_encode;
+
+// 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes of columns], 128B swizzle, OOB reads as 0.
+template <typename T>
+static int make_tmap(ResepHandle* h, CUtensorMap* m, const T* base, int64_t rows, int cols, int box_rows) {
+  const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(T)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, dt, 2, const_cast<T*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return RESEP_OK;
+}
+
+}  // namespace resep
