@@ -64,17 +64,22 @@ def kernel_work(name: str, batch: int, t: int):
     attention 76,800, out-proj 32,768, FFN 524,288."""
     L, S, chunks, M, mem_seqs = shapes(batch, t)
     rows = 16 * M + 8 * chunks                         # token-layers: 16 intra layers + 8 memory layers
-    att = 16 * chunks * 8 * 4 * 150 * 150 * 16 + 8 * sum(4 * n * n * 128 for n in mem_seqs)
+    att_intra = 16 * chunks * 8 * 4 * 150 * 150 * 16
+    att = att_intra + 8 * sum(4 * n * n * 128 for n in mem_seqs)
     if name.startswith("k_gemm_tc<bf16,bf16"):        # QKV + FFN1
         return "tensor", rows * (98_304 + 262_144)
     if name.startswith("k_gemm_tc<bf16,resid"):       # out-proj + FFN2
         return "tensor", rows * (32_768 + 262_144)
     if name.startswith("k_gemm_tc<bf16,f32"):         # output_fc
         return "tensor", M * 65_536
-    if name.startswith("k_layer_tc"):                  # fused layer kernel: every GEMM of the layer
-        return "tensor", rows * 655_360
+    if name.startswith("k_post_tc"):                   # fused out-proj + LN2 + FFN1 + ReLU + FFN2 (+ residuals)
+        return "tensor", rows * (32_768 + 524_288)
+    if name.startswith("k_qkv_tc"):                    # fused LN1 + in-projection
+        return "tensor", rows * 98_304
+    if name.startswith("k_attention_bf16_short"):      # sequences <= 160 rows (every intra chunk)
+        return "tensor", att_intra + sum(8 * 4 * n * n * 128 for n in mem_seqs if n <= 160)
     if name.startswith("k_attention"):
-        return "tensor", att
+        return "tensor", att - att_intra - sum(8 * 4 * n * n * 128 for n in mem_seqs if n <= 160) if "bf16" in name else att
     if name.startswith("k_layernorm"):
         return "hbm", 2 * rows * (512 + 256)
     if name.startswith("k_block_epilogue"):
@@ -317,9 +322,9 @@ def main():
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, times, threads = time_oracle(sds, items=4, reps=5)
+        v, times, threads = time_oracle(sds, items=BATCH, reps=5)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"4 of the {BATCH} mixtures (B=4 x {SECONDS} s), oracle fp32 eager PyTorch, 1 warm-up + median of 5 "
+               "sample": f"the whole step (B={BATCH} x {SECONDS} s, coupled), oracle fp32 eager PyTorch, 1 warm-up + median of 5 "
                          f"({sum(times):.1f} s of CPU work)", "host_cpus": os.cpu_count()}
 
     flops_step = None

@@ -384,6 +384,264 @@ k_post_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_qkv_tc: y = LayerNorm(o; g1, be1); qkv = y . Win^T + bin  (norm1 + the packed in-projection of
+// nn.MultiheadAttention) in one kernel, bf16 out.  Same building blocks as k_post_tc: the fp32 residual
+// tile arrives by TMA, dedicated LayerNorm warps (one token row per thread) store the packed bf16 result
+// to TMEM (double-buffered, so LN runs one tile ahead of the MMAs), the three 128-wide output tiles are
+// TS-form MMAs with one accumulator slot each, and the drain warps empty slot n of tile t while the tensor
+// pipe already works on tile t+1.  Output tiles leave through double-buffered swizzled staging + TMA stores.
+namespace qkvk {
+constexpr int DRAIN_THREADS = 256;               // warps 3..10: accumulator -> bias -> bf16 -> staging -> TMA store
+constexpr int LN_THREADS = 128;                  // warps 11..14: LayerNorm, one token row per thread
+constexpr int THREADS = 96 + DRAIN_THREADS + LN_THREADS;
+constexpr int TILE = 128 * 128;
+constexpr int NWST = 5;                          // weight ring depth (16 KB units)
+constexpr int OFF_OT = 0;                        // [128 x 128] fp32 residual tile (4 atoms); LN runs one tile ahead of the
+                                                 // MMAs, so a single buffer already gives a full tile of prefetch distance
+constexpr int OFF_OUT = OFF_OT + 4 * TILE;       // 2 x [128 x 128] bf16 output staging (2 atoms each)
+constexpr int OFF_W = OFF_OUT + 4 * TILE;
+constexpr int OFF_PAR = OFF_W + NWST * TILE;     // g1[128], be1[128], bin[384]
+constexpr int OFF_BAR = OFF_PAR + (2 * D + 3 * D) * 4;
+constexpr int NBAR = 2 * NWST + 2 + 4 + 6;
+constexpr int SMEM = OFF_BAR + NBAR * 8 + 16;
+constexpr int TM_ACC = 0, TM_Y2 = 384;           // 3 x 128 accumulator columns, 2 x 64 packed LN columns
+static_assert(SMEM <= 227 * 1024, "shared memory budget");
+}  // namespace qkvk
+
+struct QkvArgs {
+  const float *g1, *be1, *bin;
+  int64_t M;
+};
+
+__device__ __forceinline__ uint32_t sw128_bf16(int row, int col) {   // 16-byte chunk of 8 bf16 columns, two 64-column atoms
+  return (uint32_t)((col >> 6) * qkvk::TILE + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void drain_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(qkvk::DRAIN_THREADS) : "memory"); }
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(qkvk::THREADS, 1)
+k_qkv_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmW,
+         const __grid_constant__ CUtensorMap tmWL, const __grid_constant__ CUtensorMap tmQ, const QkvArgs args) {
+  using namespace qkvk;
+  constexpr int PARTS = SPLIT ? 2 : 1;
+  constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, UMMA_BF16, 128, 128);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* s_g1 = reinterpret_cast<float*>(smem + OFF_PAR);
+  float *s_be1 = s_g1 + D, *s_bin = s_g1 + 2 * D;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + NWST;
+  uint64_t* ot_full = bars + 2 * NWST;     // residual tile landed (TMA)
+  uint64_t* ot_empty = ot_full + 1;        // the LN warps have read it (128 arrivals)
+  uint64_t* y_full = ot_full + 2;          // [2] packed LN output stored in TMEM (128 arrivals)
+  uint64_t* y_empty = ot_full + 4;         // [2] the MMAs that read it retired (commit)
+  uint64_t* acc_full = ot_full + 6;        // [3] output tile accumulated (commit)
+  uint64_t* acc_empty = ot_full + 9;       // [3] drain warps have it in registers (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (int)((args.M + 127) / 128);
+  for (int i = threadIdx.x; i < D; i += THREADS) { s_g1[i] = args.g1[i]; s_be1[i] = args.be1[i]; }
+  for (int i = threadIdx.x; i < 3 * D; i += THREADS) s_bin[i] = args.bin[i];
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmO); prefetch_tmap(&tmW); prefetch_tmap(&tmQ);
+    if (SPLIT) prefetch_tmap(&tmWL);
+    for (int i = 0; i < NWST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(ot_full, 1); mbar_init(ot_empty, LN_THREADS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], LN_THREADS); mbar_init(&y_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], DRAIN_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                               // weight producer: Win tile (n, kb, part) in MMA order
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < m_tiles; t += gridDim.x)
+        for (int n = 0; n < 3; ++n)
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int part = 0; part < PARTS; ++part) {
+              mbar_wait(&w_empty[st], ph ^ 1);
+              mbar_arrive_expect_tx(&w_full[st], TILE);
+              tma_load_2d(smem + OFF_W + st * TILE, part ? &tmWL : &tmW, &w_full[st], kb * 64, n * 128);
+              if (++st == NWST) { st = 0; ph ^= 1; }
+            }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    if (lane == 0) {                               // residual tile producer
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+        mbar_wait(ot_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(ot_full, 4 * TILE);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(smem + OFF_OT + j * TILE, &tmO, ot_full, 32 * j, t * 128);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {                               // MMA issuer
+      int st = 0;
+      uint32_t ph = 0, it = 0;
+      for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait(&y_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        for (int n = 0; n < 3; ++n) {
+          mbar_wait(&acc_empty[n], (it & 1) ^ 1);  // slot n is used once per tile
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int part = 0; part < PARTS; ++part) {
+              mbar_wait(&w_full[st], ph);
+              tc_fence_after();
+              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem + OFF_W + st * TILE));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ts(tmem + TM_ACC + n * 128, tmem + TM_Y2 + b * 64 + kb * 32 + 8 * k, bdesc + 2 * k, IDESC,
+                             !(kb == 0 && part == 0 && k == 0));
+              umma_commit(&w_empty[st]);
+              if (++st == NWST) { st = 0; ph ^= 1; }
+            }
+          umma_commit(&acc_full[n]);
+        }
+        umma_commit(&y_empty[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 11) {
+    // ------------------------------------------------------------------ LayerNorm warps: thread == token row
+    // The row is re-read from the swizzled shared tile for each of the three passes (sum, centred sum of
+    // squares, normalise) instead of being held in 128 registers; no cross-thread exchange is needed.
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(ot_full, it & 1);
+      float sum = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float4 o4 = *reinterpret_cast<const float4*>(smem + OFF_OT + sw128_f32(r, 4 * j));
+        sum += (o4.x + o4.y) + (o4.z + o4.w);
+      }
+      const float mean = sum * (1.f / D);
+      float sq = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float4 o4 = *reinterpret_cast<const float4*>(smem + OFF_OT + sw128_f32(r, 4 * j));
+        const float d0 = o4.x - mean, d1 = o4.y - mean, d2 = o4.z - mean, d3 = o4.w - mean;
+        sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+      }
+      const float rstd = rsqrtf(sq * (1.f / D) + LN_EPS);
+      mbar_wait(&y_empty[b], ((it >> 1) & 1) ^ 1);   // the MMAs of tile it - 2 no longer read this buffer
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t p[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = half * 64 + 4 * j;
+          const float4 o4 = *reinterpret_cast<const float4*>(smem + OFF_OT + sw128_f32(r, c));
+          const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + c);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_be1 + c);
+          p[2 * j] = pack_bf16((o4.x - mean) * rstd * g4.x + b4.x, (o4.y - mean) * rstd * g4.y + b4.y);
+          p[2 * j + 1] = pack_bf16((o4.z - mean) * rstd * g4.z + b4.z, (o4.w - mean) * rstd * g4.w + b4.w);
+        }
+        tmem_st32(lane_base + TM_Y2 + b * 64 + half * 32, p);
+      }
+      mbar_arrive(ot_empty);                        // tile buffer may be refilled
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&y_full[b]);
+    }
+  } else {
+    // ------------------------------------------------------------------ drain warps: (row r, column half hf)
+    const int ew = warp - 3;
+    const int q = warp & 3;
+    const int hf = ew >> 2;
+    const int r = q * 32 + lane;
+    const int cb = hf * 64;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const bool elected = ew == 0 && lane == 0;
+    uint32_t it = 0, nstore = 0;
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+#pragma unroll 1
+      for (int n = 0; n < 3; ++n, ++nstore) {
+        uint8_t* out = smem + OFF_OUT + (nstore & 1) * 2 * TILE;
+        mbar_wait(&acc_full[n], it & 1);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld32(lane_base + TM_ACC + n * 128 + cb, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(lane_base + TM_ACC + n * 128 + cb + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[n]);
+        if (elected) tma_store_wait_read<1>();     // the store issued two output tiles ago has read this staging buffer
+        drain_bar_sync();
+        const float* bias = s_bin + n * 128 + cb;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * j);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * j + 4);
+          *reinterpret_cast<uint4*>(out + sw128_bf16(r, cb + 8 * j)) =
+              make_uint4(pack_bf16(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y),
+                         pack_bf16(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w),
+                         pack_bf16(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y),
+                         pack_bf16(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w));
+        }
+        fence_proxy_async();
+        drain_bar_sync();
+        if (elected) {
+          tma_store_2d(&tmQ, out, n * 128, t * 128);
+          tma_store_2d(&tmQ, out + TILE, n * 128 + 64, t * 128);
+          tma_store_commit();
+        }
+      }
+    }
+    if (elected) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st) {
+  if (rows <= 0) return RESEP_OK;
+  ProfScope prof_scope(h, "k_qkv_tc", st);
+  const bool split = h->w16_mode == 1;
+  CUtensorMap tmO, tmW, tmWL, tmQ;
+  int rc;
+  if ((rc = make_tmap<float>(h, &tmO, o, rows, D, 128))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW, lw.in_w_bf, 3 * D, D, 128))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmWL, lw.in_w_bl, 3 * D, D, 128))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmQ, qkv, rows, 3 * D, 128))) return rc;
+  QkvArgs a{lw.norm1_w, lw.norm1_b, lw.in_b, rows};
+  const int tiles = (int)((rows + 127) / 128);
+  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  if (split) {
+    RESEP_CUDA(h, cudaFuncSetAttribute(k_qkv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qkvk::SMEM));
+    k_qkv_tc<true><<<grid, qkvk::THREADS, qkvk::SMEM, st>>>(tmO, tmW, tmWL, tmQ, a);
+  } else {
+    RESEP_CUDA(h, cudaFuncSetAttribute(k_qkv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qkvk::SMEM));
+    k_qkv_tc<false><<<grid, qkvk::THREADS, qkvk::SMEM, st>>>(tmO, tmW, tmWL, tmQ, a);
+  }
+  RESEP_LAUNCH_CHECK(h, "k_qkv_tc");
+  return RESEP_OK;
+}
+
 long long* g_post_trace = nullptr;
 
 int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st) {

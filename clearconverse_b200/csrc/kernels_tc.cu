@@ -412,16 +412,161 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
   }
 }
 
+// Short-sequence attention (len <= 160: every intra chunk and most memory sequences), one CTA per
+// (sequence, head), 5 warps x 2 m16 query tiles.  Two passes over the keys with Q.K^T recomputed
+// (19 extra HMMA per tile, the tensor pipe is nearly idle here) instead of holding the 16 x 160 score
+// tile in registers: ~50 registers per thread, so 6+ CTAs are resident per SM and the MUFU.EX2 /
+// LDS / HMMA latencies overlap across warps.  Fragments come from ldmatrix (K as is, V transposed
+// by the .trans form), rows padded to 48 B so the 8 x 16 B row reads are bank-conflict free.
+// Per score: FMNMX (pass 1); FFMA + MUFU.EX2 + FADD + half a pack (pass 2) -- the MUFU unit (16/clk/SM)
+// is the floor.
+constexpr int AS_ROW = 24;   // halves per staged K / V row (16 used)
+__global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx,
+                                                                 int seq_len, const int* __restrict__ seq_off) {
+  __shared__ __align__(16) bf16 Ks[160 * AS_ROW];
+  __shared__ __align__(16) bf16 Vs[160 * AS_ROW];
+  int off, len;
+  if (seq_off != nullptr) {
+    off = seq_off[blockIdx.x];
+    len = seq_off[blockIdx.x + 1] - off;
+  } else {
+    off = blockIdx.x * seq_len;
+    len = seq_len;
+  }
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
+  {  // stage one key / value row per thread (rows past the sequence are zero)
+    const int key = threadIdx.x;
+    uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+    if (key < len) {
+      const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
+      k0 = p[0]; k1 = p[1];
+      const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
+      v0 = pv[0]; v1 = pv[1];
+    }
+    uint4* kd = reinterpret_cast<uint4*>(Ks + key * AS_ROW);
+    uint4* vd = reinterpret_cast<uint4*>(Vs + key * AS_ROW);
+    kd[0] = k0; kd[1] = k1;
+    vd[0] = v0; vd[1] = v1;
+  }
+  __syncthreads();
+  const int nkk = (len + 15) >> 4;                    // 16-key blocks holding at least one valid key
+  constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
+  // ldmatrix lane addressing: matrix m = lane / 8, row lane % 8
+  const int lm = lane >> 3, lr = lane & 7;
+  const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * AS_ROW + (lm & 1) * 8;   // K: m0/m1 = dh halves of tile A, m2/m3 of tile B
+  const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * AS_ROW + (lm >> 1) * 8;   // V^T: m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int row0 = warp * 32 + mt * 16;
+    if (row0 >= len) break;                            // warp-uniform
+    uint32_t qa[4];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = row0 + g + hh * 8;
+      uint32_t lo = 0, hi = 0;
+      if (r < len) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(qbase + (int64_t)r * (3 * D));
+        lo = p[t4];
+        hi = p[t4 + 4];
+      }
+      qa[hh] = lo;
+      qa[hh + 2] = hi;
+    }
+    // ---- pass 1: row maxima of the raw scores
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 2
+    for (int kk = 0; kk < nkk; ++kk) {
+      uint32_t kf[4];
+      ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(s0, qa, kf[0], kf[1]);
+      mma_bf16_16816(s1, qa, kf[2], kf[3]);
+      if (kk * 16 + 16 > len) {                        // last block: mask keys past the sequence
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+        if (c + 1 >= len) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+        if (c + 8 >= len) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
+        if (c + 9 >= len) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
+      }
+      mx0 = fmaxf(mx0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
+      mx1 = fmaxf(mx1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
+    // ---- pass 2: p = exp2(s * SC - max * SC), row sums, O += P . V
+    float l0 = 0.f, l1 = 0.f;
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int kk = 0; kk < nkk; ++kk) {
+      uint32_t kf[4], vf[4];
+      ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
+      ldmatrix_x4_trans(vf, v_lane + kk * 16 * AS_ROW);
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(s0, qa, kf[0], kf[1]);
+      mma_bf16_16816(s1, qa, kf[2], kf[3]);
+      s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
+      s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
+      s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
+      s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
+      if (kk * 16 + 16 > len) {
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
+        if (c + 1 >= len) { s0[1] = 0.f; s0[3] = 0.f; }
+        if (c + 8 >= len) { s1[0] = 0.f; s1[2] = 0.f; }
+        if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
+      }
+      l0 += (s0[0] + s0[1]) + (s1[0] + s1[1]);
+      l1 += (s0[2] + s0[3]) + (s1[2] + s1[3]);
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s0[0], s0[1]);
+      pa[1] = pack_bf16(s0[2], s0[3]);
+      pa[2] = pack_bf16(s1[0], s1[1]);
+      pa[3] = pack_bf16(s1[2], s1[3]);
+      mma_bf16_16816(o0, pa, vf[0], vf[1]);
+      mma_bf16_16816(o1, pa, vf[2], vf[3]);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = row0 + g, r1 = row0 + g + 8;
+    if (r0 < len) {
+      bf16* op = ctx + (int64_t)(off + r0) * D + head * DH + 2 * t4;
+      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[0] * i0, o0[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[0] * i0, o1[1] * i0);
+    }
+    if (r1 < len) {
+      bf16* op = ctx + (int64_t)(off + r1) * D + head * DH + 2 * t4;
+      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[2] * i1, o0[3] * i1);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[2] * i1, o1[3] * i1);
+    }
+  }
+}
+
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
-                                 const int* tile_seq, const int* tile_q0, int n_tiles128, cudaStream_t st) {
-  ProfScope prof_scope(h, "k_attention_bf16", st);
+                                 const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st) {
+  ProfScope prof_scope(h, (tile_seq == nullptr ? seq_len : max_len) <= 160 ? "k_attention_bf16_short" : "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
   // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
   // of the next tile with identical results).
   if (tile_seq == nullptr) {
     if (n_seq == 0) return RESEP_OK;
-    const int tps = (seq_len + AKT - 1) / AKT;
-    k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
+    if (seq_len <= 160) {
+      k_attention_bf16_short<<<dim3((unsigned)n_seq, NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr);
+    } else {
+      const int tps = (seq_len + AKT - 1) / AKT;
+      k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
+    }
+  } else if (max_len <= 160) {
+    if (n_seq == 0) return RESEP_OK;
+    k_attention_bf16_short<<<dim3((unsigned)n_seq, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off);
   } else {
     if (n_tiles128 == 0) return RESEP_OK;
     k_attention_bf16<<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
@@ -491,16 +636,20 @@ int tc_linear_test(ResepHandle* h, const float* A, const float* W, const float* 
 //   bf16 mode: y / qkv / ctx / hid are bf16 (half the bytes of the fp32 scratch regions they live in)
 //   tf32 mode: fp32 buffers holding tf32-rounded values; attention uses the fp32 kernel
 int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
-                 const int* tile_seq, const int* tile_q0, int n_tiles, float* y, float* qkv, float* ctx, float* hid,
+                 const int* tile_seq, const int* tile_q0, int n_tiles, int max_seq_len, float* y, float* qkv, float* ctx, float* hid,
                  int precision, cudaStream_t st) {
   int rc;
   if (precision == RESEP_PREC_BF16) {
     bf16 *yb = reinterpret_cast<bf16*>(y), *qb = reinterpret_cast<bf16*>(qkv), *cb = reinterpret_cast<bf16*>(ctx),
          *hb = reinterpret_cast<bf16*>(hid);
-    if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
-    if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
-    if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st))) return rc;
     static const bool fused = !(getenv("RESEP_FUSED") && getenv("RESEP_FUSED")[0] == '0');
+    if (fused) {
+      if ((rc = launch_qkv_tc(h, lw, o, qb, rows, st))) return rc;   // norm1 + in-projection in one kernel
+    } else {
+      if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
+      if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
+    }
+    if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st))) return rc;
     if (fused) return launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
     if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;
     if ((rc = launch_layernorm<bf16>(h, o, lw.norm2_w, lw.norm2_b, yb, rows, st))) return rc;

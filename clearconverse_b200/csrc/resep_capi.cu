@@ -297,6 +297,7 @@ struct SeqDesc {          // the sequences one transformer block runs over
   const int* tile_seq;    // attention query tiles of the ragged case
   const int* tile_q0;
   int n_tiles;
+  int max_len;            // longest sequence
 };
 
 static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc& sd, const Workspace& ws, int precision,
@@ -313,7 +314,7 @@ static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc
     if ((rc = launch_gemm_f32(h, ws.hid, lw.f2_w, lw.f2_b, o, o, sd.rows, D, FFN, false, st))) return rc;
     return RESEP_OK;
   }
-  return tc_run_layer(h, lw, o, sd.rows, sd.n_seq, sd.seq_len, sd.seq_off, sd.tile_seq, sd.tile_q0, sd.n_tiles, ws.y,
+  return tc_run_layer(h, lw, o, sd.rows, sd.n_seq, sd.seq_len, sd.seq_off, sd.tile_seq, sd.tile_q0, sd.n_tiles, sd.max_len, ws.y,
                       ws.qkv, ws.ctx, ws.hid, precision, st);
 }
 
@@ -348,9 +349,9 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
   if ((rc = launch_encoder_chunked(h, mix, *p, ws.x0, st))) return rc;
   if (dbg && dbg->enc) RESEP_CUDA(h, cudaMemcpyAsync(dbg->enc, ws.x0, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
-  SeqDesc intra{p->M, (int)p->n_chunks, CHUNK, nullptr, nullptr, nullptr, nullptr, 0};
+  SeqDesc intra{p->M, (int)p->n_chunks, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK};
   SeqDesc mem{p->n_chunks, p->n_mem_seq, 0, p->d_mem_seq_off, p->d_mem_pos, p->d_mem_tile_seq, p->d_mem_tile_q0,
-              p->n_mem_tiles};
+              p->n_mem_tiles, p->max_mem_len};
   if (p->n_mem_seq == 1) {   // a single sequence is the equal-length case
     mem.seq_len = (int)p->n_chunks; mem.seq_off = nullptr; mem.pos = nullptr; mem.tile_seq = nullptr; mem.tile_q0 = nullptr;
   }
@@ -545,7 +546,7 @@ int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, i
   int rc;
   if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
   const int blk = block == 2 ? 2 : block;
-  SeqDesc sd{rows, n_seq, seq_len, nullptr, nullptr, nullptr, nullptr, 0};
+  SeqDesc sd{rows, n_seq, seq_len, nullptr, nullptr, nullptr, nullptr, 0, seq_len};
   return run_layer(h, h->w.blk[blk].layers[layer], x, sd, ws, precision, static_cast<cudaStream_t>(stream));
 }
 

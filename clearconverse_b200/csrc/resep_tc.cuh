@@ -7,12 +7,15 @@ namespace resep {
 // One TransformerEncoderLayer on o [rows,128] (fp32 residual stream, updated in place) with the
 // GEMMs and attention on tensor cores.  y/qkv/ctx/hid are scratch regions of the workspace.
 int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
-                 const int* tile_seq, const int* tile_q0, int n_tiles, float* y, float* qkv, float* ctx, float* hid,
+                 const int* tile_seq, const int* tile_q0, int n_tiles, int max_seq_len, float* y, float* qkv, float* ctx, float* hid,
                  int precision, cudaStream_t st);
 
 // Fused post-attention half of a layer (kernels_layer.cu), bf16 mode:
 //   o <- o' + W2 relu(W1 LN2(o') + b1) + b2,  o' = o + ctx . Wo^T + bo      (o fp32 in place, ctx bf16)
 int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st);
+
+// Fused norm1 + in-projection (kernels_layer.cu), bf16 mode: qkv[rows,384] = LN1(o) . Win^T + bin
+int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st);
 
 extern long long* g_post_trace;   // development aid: clock trace buffer of k_post_tc (null unless RESEP_TRACE is set)
 
