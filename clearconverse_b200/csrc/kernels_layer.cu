@@ -70,14 +70,15 @@ __device__ __forceinline__ uint32_t sw128_f32(int row, int col) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(post::EPI_THREADS) : "memory"); }
 
-template <bool SPLIT>
+template <bool SPLIT, bool SPLIT_FFN>
 __global__ void __launch_bounds__(post::THREADS, 1)
 k_post_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmO,
           const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWoL,
           const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW1L,
           const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW2L, const PostArgs args) {
   using namespace post;
-  constexpr int PARTS = SPLIT ? 2 : 1;
+  constexpr int PARTS = SPLIT ? 2 : 1;          // out-proj weight operand: bf16 hi (+ lo)
+  constexpr int FPARTS = SPLIT_FFN ? 2 : 1;     // FFN weight operands
   constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, UMMA_BF16, 128, 128);
 
   // 128B-swizzled tiles need 1024-byte alignment; declaring it on the dynamic window keeps every access
@@ -110,7 +111,8 @@ k_post_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUt
   for (int i = threadIdx.x; i < FFN; i += THREADS) s_b1[i] = args.b1[i];
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmCtx); prefetch_tmap(&tmO); prefetch_tmap(&tmWo); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
-    if (SPLIT) { prefetch_tmap(&tmWoL); prefetch_tmap(&tmW1L); prefetch_tmap(&tmW2L); }
+    if (SPLIT) prefetch_tmap(&tmWoL);
+    if (SPLIT_FFN) { prefetch_tmap(&tmW1L); prefetch_tmap(&tmW2L); }
     for (int i = 0; i < NWST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(o_full, 1); mbar_init(ot_empty, 1);
     mbar_init(y_full, EPI_THREADS);
@@ -129,20 +131,19 @@ k_post_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUt
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1) {
-#pragma unroll
-        for (int part = 0; part < PARTS; ++part) {
+      auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1, int parts) {
+        for (int part = 0; part < parts; ++part) {
           mbar_wait(&w_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&w_full[st], TILE);
           tma_load_2d(smem + OFF_W + st * TILE, part ? lo : hi, &w_full[st], c0, c1);
           if (++st == NWST) { st = 0; ph ^= 1; }
         }
       };
-      auto put_f1 = [&](int c) { put(&tmW1, &tmW1L, 0, c * 128); put(&tmW1, &tmW1L, 64, c * 128); };
-      auto put_f2 = [&](int c) { put(&tmW2, &tmW2L, c * 128, 0); put(&tmW2, &tmW2L, c * 128 + 64, 0); };
+      auto put_f1 = [&](int c) { put(&tmW1, &tmW1L, 0, c * 128, FPARTS); put(&tmW1, &tmW1L, 64, c * 128, FPARTS); };
+      auto put_f2 = [&](int c) { put(&tmW2, &tmW2L, c * 128, 0, FPARTS); put(&tmW2, &tmW2L, c * 128 + 64, 0, FPARTS); };
       for (int t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-        put(&tmWo, &tmWoL, 0, 0);
-        put(&tmWo, &tmWoL, 64, 0);
+        put(&tmWo, &tmWoL, 0, 0, PARTS);
+        put(&tmWo, &tmWoL, 64, 0, PARTS);
         put_f1(0);
         put_f1(1);
         for (int c = 0; c < NCHUNK; ++c) {
@@ -203,14 +204,14 @@ k_post_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUt
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int part = 0; part < PARTS; ++part) unit_ts(d, tmem + TM_Y2 + 32 * kb, kb == 0 && part == 0);
+          for (int part = 0; part < FPARTS; ++part) unit_ts(d, tmem + TM_Y2 + 32 * kb, kb == 0 && part == 0);
       };
       // FFN2 chunk: Y += relu(H) . W2_chunk^T; the packed chunk sits in columns [0,32) and [64,96) of its accumulator
       auto ffn2 = [&](uint32_t h) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int part = 0; part < PARTS; ++part) unit_ts(tmem + TM_Y, h + 64 * kb, false);
+          for (int part = 0; part < FPARTS; ++part) unit_ts(tmem + TM_Y, h + 64 * kb, false);
       };
       const bool tr = args.trace != nullptr && blockIdx.x == 0;
       int ti = 0;
@@ -621,7 +622,7 @@ k_qkv_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtens
 int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st) {
   if (rows <= 0) return RESEP_OK;
   ProfScope prof_scope(h, "k_qkv_tc", st);
-  const bool split = h->w16_mode == 1;
+  const bool split = h->w16_mode >= 1;
   CUtensorMap tmO, tmW, tmWL, tmQ;
   int rc;
   if ((rc = make_tmap<float>(h, &tmO, o, rows, D, 128))) return rc;
@@ -647,7 +648,7 @@ long long* g_post_trace = nullptr;
 int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st) {
   if (rows <= 0) return RESEP_OK;
   ProfScope prof_scope(h, "k_post_tc", st);
-  const bool split = h->w16_mode == 1;
+  const bool split = h->w16_mode >= 1, split_ffn = h->w16_mode == 1;
   CUtensorMap tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L;
   int rc;
   if ((rc = make_tmap<bf16>(h, &tmCtx, ctx, rows, D, 128))) return rc;
@@ -664,13 +665,9 @@ int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o
   if (trace_buf) g_post_trace = trace_buf;
   const int tiles = (int)((rows + 127) / 128);
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  if (split) {
-    RESEP_CUDA(h, cudaFuncSetAttribute(k_post_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, post::SMEM));
-    k_post_tc<true><<<grid, post::THREADS, post::SMEM, st>>>(tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L, a);
-  } else {
-    RESEP_CUDA(h, cudaFuncSetAttribute(k_post_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, post::SMEM));
-    k_post_tc<false><<<grid, post::THREADS, post::SMEM, st>>>(tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L, a);
-  }
+  auto kern = split_ffn ? k_post_tc<true, true> : split ? k_post_tc<true, false> : k_post_tc<false, false>;
+  RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, post::SMEM));
+  kern<<<grid, post::THREADS, post::SMEM, st>>>(tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L, a);
   RESEP_LAUNCH_CHECK(h, "k_post_tc");
   return RESEP_OK;
 }

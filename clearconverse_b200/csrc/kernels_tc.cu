@@ -244,11 +244,11 @@ static int launch_gemm_tc(ResepHandle* h, const TIn* A, const TIn* W, const floa
   return RESEP_OK;
 }
 
-// bf16-activation GEMM with the handle's weight operand mode: 1 = W as bf16 hi + lo (default), 0 = bf16(W) only
+// bf16-activation GEMM; mode != 0: W as bf16 hi + lo (two MMAs per K-slice), 0: bf16(W) only
 template <int EPI>
 static int gemm_bf16(ResepHandle* h, int mode, const bf16* A, const bf16* W, const bf16* Wlo, const float* bias, void* out,
                      int64_t M, int N, int K, bool relu, cudaStream_t st) {
-  if (mode == 1) return launch_gemm_tc<bf16, EPI, true>(h, A, W, bias, out, M, N, K, relu, st, Wlo);
+  if (mode != 0) return launch_gemm_tc<bf16, EPI, true>(h, A, W, bias, out, M, N, K, relu, st, Wlo);
   return launch_gemm_tc<bf16, EPI, false>(h, A, W, bias, out, M, N, K, relu, st);
 }
 
@@ -653,8 +653,8 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
     if (fused) return launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
     if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;
     if ((rc = launch_layernorm<bf16>(h, o, lw.norm2_w, lw.norm2_b, yb, rows, st))) return rc;
-    if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.f1_w_bf, lw.f1_w_bl, lw.f1_b, hb, rows, FFN, D, true, st))) return rc;
-    if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, hb, lw.f2_w_bf, lw.f2_w_bl, lw.f2_b, o, rows, D, FFN, false, st))) return rc;
+    if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode == 1, yb, lw.f1_w_bf, lw.f1_w_bl, lw.f1_b, hb, rows, FFN, D, true, st))) return rc;
+    if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode == 1, hb, lw.f2_w_bf, lw.f2_w_bl, lw.f2_b, o, rows, D, FFN, false, st))) return rc;
     return RESEP_OK;
   }
   // tf32: operands are fp32 in memory; the tensor core reads the top 19 bits, so every producer rounds

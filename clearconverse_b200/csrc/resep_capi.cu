@@ -414,7 +414,8 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
   h->sm_count = prop.multiProcessorCount;
   if (const char* m = getenv("RESEP_W16")) {   // weight operand of the bf16 mode (see DESIGN.md "precision modes")
     if (!strcmp(m, "bf16")) h->w16_mode = 0;          // single rounded bf16 weight: fails the SI-SNR gate
-    else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;
+    else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;   // every weight as hi + lo
+    else if (!strcmp(m, "mixed")) h->w16_mode = 2;    // default
   }
   int rc = upload_weights(h, w);
   if (rc) {

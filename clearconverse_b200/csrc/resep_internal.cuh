@@ -86,7 +86,9 @@ struct ResepHandle {
   std::vector<resep::Plan*> plans;
   uint64_t tick = 0;
   int64_t launches = 0;
-  int w16_mode = 1;       // RESEP_PREC_BF16 weight operand: 1 = bf16 hi + lo (two MMAs per K-slice), 0 = bf16(W) only
+  // RESEP_PREC_BF16 weight operands (DESIGN.md "precision modes"): 2 = in-proj / out-proj / output_fc as bf16 hi + lo
+  // (two MMAs per K-slice), FFN weights as one rounded bf16 (default); 1 = every weight hi + lo; 0 = bf16(W) only
+  int w16_mode = 2;
   bool prof_on = false;   // resep_profile(): bracket every launch with CUDA events
   struct ProfRec { cudaEvent_t a, b; const char* name; };
   std::vector<ProfRec> prof;

@@ -13,7 +13,7 @@ sds = oracle.component_state_dicts()
 cases = [synth_batch(2, 2000, 2), synth_batch(1, 32000, 1), synth_batch(3, 9000, 5), synth_batch(16, 32000, 2)]
 wants = [oracle.separate_batch(x) for x in cases]
 # linear hook, precision codes 2,3,4
-for mode in ("bf16", "bf16x2", "fp16"):
+for mode in ("bf16", "bf16x2", "mixed"):
     os.environ["RESEP_W16"] = mode
     sep = SepformerSeparation(sds, device="cuda:0", precision="bf16")
     row = []
