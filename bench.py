@@ -72,7 +72,7 @@ def kernel_work(name: str, batch: int, t: int):
         return "tensor", rows * (32_768 + 262_144)
     if name.startswith("k_gemm_tc<bf16,f32"):         # output_fc
         return "tensor", M * 65_536
-    if name.startswith("k_post_tc"):                   # fused out-proj + LN2 + FFN1 + ReLU + FFN2 (+ residuals)
+    if name.startswith("k_post"):                      # fused out-proj + LN2 + FFN1 + ReLU + FFN2 (+ residuals); k_post2_tc = CTA-pair version
         return "tensor", rows * (32_768 + 524_288)
     if name.startswith("k_qkv_tc"):                    # fused LN1 + in-projection
         return "tensor", rows * 98_304
@@ -336,7 +336,7 @@ def main():
         "ms_per_step": total_ms.item() / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "seconds_per_item": SECONDS, "sample_rate": SAMPLE_RATE,
-                   "batch_mode": "coupled", "weights": "random-init (seed 0), bf16 hi+lo operands, fp32 accumulate",
+                   "batch_mode": "coupled", "weights": "random-init (seed 0); bf16 operands (in-proj / out-proj / output_fc weights as bf16 hi+lo, FFN weights single bf16), fp32 accumulate",
                    "l2": "256 MiB buffer written between timed steps (L2 flush)", "parallelism": f"replicated x{world}, no collective"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * T * 4, "d2h_bytes_per_step": BATCH * T * 2 * 4},

@@ -650,7 +650,8 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
       if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
     }
     if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st))) return rc;
-    if (fused) return launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
+    static const bool post2 = !(getenv("RESEP_POST2") && getenv("RESEP_POST2")[0] == '0');
+    if (fused) return post2 ? launch_post2_tc(h, lw, cb, o, rows, st) : launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
     if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;
     if ((rc = launch_layernorm<bf16>(h, o, lw.norm2_w, lw.norm2_b, yb, rows, st))) return rc;
     if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode == 1, yb, lw.f1_w_bf, lw.f1_w_bl, lw.f1_b, hb, rows, FFN, D, true, st))) return rc;

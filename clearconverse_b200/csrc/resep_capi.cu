@@ -95,6 +95,8 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   Tf(d.fc_w_tf, d.fc_w_lo, w->fc_w, NSPK * D * D);
   d.pe_rows = w->pe_rows;
   const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
+  constexpr size_t POST_PAR = 4 * D + FFN;
+  h->host_par.assign(3 * NL * POST_PAR, 0.f);
   for (int b = 0; b < 3; ++b) {
     const ResepBlockWeights& sb = *src_blocks[b];
     BlockDev& db = d.blk[b];
@@ -107,6 +109,12 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
       if (!s.norm1_w || !s.norm1_b || !s.in_proj_w || !s.in_proj_b || !s.out_proj_w || !s.out_proj_b || !s.norm2_w ||
           !s.norm2_b || !s.ffn1_w || !s.ffn1_b || !s.ffn2_w || !s.ffn2_b)
         return set_err(h, RESEP_EINVAL, "null layer weight");
+      {
+        float* hp = h->host_par.data() + (size_t)(b * NL + l) * POST_PAR;
+        std::memcpy(hp, s.out_proj_b, D * 4); std::memcpy(hp + D, s.norm2_w, D * 4); std::memcpy(hp + 2 * D, s.norm2_b, D * 4);
+        std::memcpy(hp + 3 * D, s.ffn2_b, D * 4); std::memcpy(hp + 4 * D, s.ffn1_b, FFN * 4);
+        t.h_post_par = hp;
+      }
       F(t.norm1_w, s.norm1_w, D); F(t.norm1_b, s.norm1_b, D);
       F(t.in_w, s.in_proj_w, 3 * D * D); F(t.in_b, s.in_proj_b, 3 * D);
       F(t.out_w, s.out_proj_w, D * D); F(t.out_b, s.out_proj_b, D);
@@ -454,11 +462,11 @@ const char* resep_last_error(const ResepHandle* h) { return h ? h->err.c_str() :
 
 int64_t resep_launch_count(const ResepHandle* h) { return h ? h->launches : 0; }
 
-// development aid (not in the public header): copy the k_post_tc clock trace of CTA 0 to `out[128]`
+// development aid (not in the public header): copy the k_post2_tc clock trace of CTA 0 to `out[1536]`
 extern "C" int resep_debug_trace(long long* out) {
   if (!resep::g_post_trace) return -1;
   cudaDeviceSynchronize();
-  return cudaMemcpy(out, resep::g_post_trace, 256 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+  return cudaMemcpy(out, resep::g_post_trace, 1536 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
 
 int resep_profile(ResepHandle* h, int enable) {

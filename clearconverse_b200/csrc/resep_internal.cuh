@@ -33,6 +33,9 @@ struct LayerDev {
   const bf16 *in_w_bl, *out_w_bl, *f1_w_bl, *f2_w_bl;       // bf16(W - bf16(W)): low part for the split-weight mode
   const float *in_w_tf, *out_w_tf, *f1_w_tf, *f2_w_tf;      // tf32-rounded fp32 copies (RESEP_PREC_TF32): hi part
   const float *in_w_lo, *out_w_lo, *f1_w_lo, *f2_w_lo;      // tf32(W - hi): the TF32 mode runs W = hi + lo
+  // HOST copy of out_b[128], norm2_w[128], norm2_b[128], f2_b[128], f1_b[1024]: k_post2_tc takes them as kernel
+  // parameters (constant bank) so that its epilogues do not spend shared-memory bandwidth on broadcast loads
+  const float* h_post_par;
 };
 struct BlockDev {
   LayerDev layers[NL];
@@ -81,6 +84,7 @@ struct ResepHandle {
   int sm_count = 148;
   std::string err;
   void* arena = nullptr;  // all weights, one allocation
+  std::vector<float> host_par;   // per layer: the 1,536 floats LayerDev::h_post_par points at
   size_t arena_bytes = 0;
   resep::WeightsDev w;
   std::vector<resep::Plan*> plans;

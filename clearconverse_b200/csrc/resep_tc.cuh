@@ -14,6 +14,9 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
 //   o <- o' + W2 relu(W1 LN2(o') + b1) + b2,  o' = o + ctx . Wo^T + bo      (o fp32 in place, ctx bf16)
 int launch_post_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st);
 
+// The same on CTA pairs (tcgen05 cta_group::2, kernels_post2.cu): the default; RESEP_POST2=0 selects the 1-CTA kernel
+int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st);
+
 // Fused norm1 + in-projection (kernels_layer.cu), bf16 mode: qkv[rows,384] = LN1(o) . Win^T + bin
 int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st);
 
