@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -437,7 +438,25 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
-  {  // stage one key / value row per thread (rows past the sequence are zero)
+  __shared__ float s_kmax[5];
+  // Q fragments of this warp's two m16 tiles, requested before the K / V rows so that the CTA pays one global-memory
+  // latency, not three (rows past the sequence read as zero)
+  uint32_t qf[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = warp * 32 + mt * 16 + g + hh * 8;
+      uint32_t lo = 0, hi = 0;
+      if (r < len) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(qbase + (int64_t)r * (3 * D));
+        lo = __ldg(p + t4);
+        hi = __ldg(p + t4 + 4);
+      }
+      qf[mt][hh] = lo;
+      qf[mt][hh + 2] = hi;
+    }
+  {  // stage one key / value row per thread (rows past the sequence are zero); squared norm of the key row
     const int key = threadIdx.x;
     uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
     if (key < len) {
@@ -450,41 +469,61 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
     uint4* vd = reinterpret_cast<uint4*>(Vs + key * AS_ROW);
     kd[0] = k0; kd[1] = k1;
     vd[0] = v0; vd[1] = v1;
+    const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float kn2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
+      kn2 = fmaf(f.x, f.x, kn2);
+      kn2 = fmaf(f.y, f.y, kn2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
+    if (lane == 0) s_kmax[warp] = kn2;
   }
   __syncthreads();
+  const float kmax2 = fmaxf(fmaxf(fmaxf(s_kmax[0], s_kmax[1]), fmaxf(s_kmax[2], s_kmax[3])), s_kmax[4]);
   const int nkk = (len + 15) >> 4;                    // 16-key blocks holding at least one valid key
   constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
   // ldmatrix lane addressing: matrix m = lane / 8, row lane % 8
   const int lm = lane >> 3, lr = lane & 7;
   const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * AS_ROW + (lm & 1) * 8;   // K: m0/m1 = dh halves of tile A, m2/m3 of tile B
   const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * AS_ROW + (lm >> 1) * 8;   // V^T: m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
-#pragma unroll 1
+  constexpr uint32_t ONES = 0x3F803F80u;              // bf16 (1.0, 1.0): B fragment of an all-ones [16 keys x 8] matrix
+#pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     const int row0 = warp * 32 + mt * 16;
     if (row0 >= len) break;                            // warp-uniform
-    uint32_t qa[4];
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int r = row0 + g + hh * 8;
-      uint32_t lo = 0, hi = 0;
-      if (r < len) {
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(qbase + (int64_t)r * (3 * D));
-        lo = p[t4];
-        hi = p[t4 + 4];
-      }
-      qa[hh] = lo;
-      qa[hh + 2] = hi;
+    const uint32_t (&qa)[4] = qf[mt];
+    // Softmax stabiliser.  Any m_i >= max_j s_ij gives the same softmax; by Cauchy-Schwarz s_ij <= |q_i| |k_j| so
+    // m_i = |q_i| * max_j |k_j| (computed from norms: no pass over the scores) never overflows.  Scores lie in
+    // [-m_i, m_i], so exp((s_ij - m_i) / 4) cannot flush to zero as long as 2 m_i / 4 < 80 nats; a warp whose rows
+    // violate that (never seen with LayerNorm'ed inputs) takes the exact row-maximum pass instead.
+    float qn0, qn1;
+    {
+      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[0]));
+      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[1]));
+      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[2]));
+      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[3]));
+      qn0 = a0.x * a0.x + a0.y * a0.y + a2.x * a2.x + a2.y * a2.y;     // row g:     dims 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
+      qn1 = a1.x * a1.x + a1.y * a1.y + a3.x * a3.x + a3.y * a3.y;     // row g + 8
+      qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
+      qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
-    // ---- pass 1: row maxima of the raw scores
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 2
-    for (int kk = 0; kk < nkk; ++kk) {
+    float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;   // upper bounds of the raw scores
+    float mb = fmaxf(mx0, mx1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    // Only the last 16-key block can hold keys past the sequence: it is peeled off (MASK = true), so the other
+    // blocks carry no compare / select instructions.
+    auto max_block = [&](int kk, auto mask_c) {
+      constexpr bool MASK = decltype(mask_c)::value;
       uint32_t kf[4];
       ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
-      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816(s0, qa, kf[0], kf[1]);
-      mma_bf16_16816(s1, qa, kf[2], kf[3]);
-      if (kk * 16 + 16 > len) {                        // last block: mask keys past the sequence
+      float s0[4], s1[4];
+      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
+      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
+      if (MASK) {
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
         if (c + 1 >= len) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
@@ -493,36 +532,41 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
       }
       mx0 = fmaxf(mx0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
       mx1 = fmaxf(mx1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
+    };
+    if (!(mb * 0.5f < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs
+      // ---- exact pass: row maxima of the raw scores
+      mx0 = -INFINITY; mx1 = -INFINITY;
+#pragma unroll 1
+      for (int kk = 0; kk < nkk - 1; ++kk) max_block(kk, std::false_type{});
+      max_block(nkk - 1, std::true_type{});
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
-    // ---- pass 2: p = exp2(s * SC - max * SC), row sums, O += P . V
-    float l0 = 0.f, l1 = 0.f;
-    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int kk = 0; kk < nkk; ++kk) {
+    // ---- pass 2: p = exp2(s * SC - max * SC); O += P . V; row sums of the bf16-rounded P from a third MMA against an
+    // all-ones B fragment (every column of that accumulator is the row sum, so no add chain and no shuffle)
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, ol[4] = {0.f, 0.f, 0.f, 0.f};
+    auto pv_block = [&](int kk, auto mask_c) {
+      constexpr bool MASK = decltype(mask_c)::value;
       uint32_t kf[4], vf[4];
       ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
       ldmatrix_x4_trans(vf, v_lane + kk * 16 * AS_ROW);
-      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816(s0, qa, kf[0], kf[1]);
-      mma_bf16_16816(s1, qa, kf[2], kf[3]);
+      float s0[4], s1[4];
+      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
+      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
       s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
       s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
       s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
       s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
-      if (kk * 16 + 16 > len) {
+      if (MASK) {
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
         if (c + 1 >= len) { s0[1] = 0.f; s0[3] = 0.f; }
         if (c + 8 >= len) { s1[0] = 0.f; s1[2] = 0.f; }
         if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
       }
-      l0 += (s0[0] + s0[1]) + (s1[0] + s1[1]);
-      l1 += (s0[2] + s0[3]) + (s1[2] + s1[3]);
       uint32_t pa[4];
       pa[0] = pack_bf16(s0[0], s0[1]);
       pa[1] = pack_bf16(s0[2], s0[3]);
@@ -530,12 +574,12 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
       pa[3] = pack_bf16(s1[2], s1[3]);
       mma_bf16_16816(o0, pa, vf[0], vf[1]);
       mma_bf16_16816(o1, pa, vf[2], vf[3]);
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
+      mma_bf16_16816(ol, pa, ONES, ONES);
+    };
+#pragma unroll 3
+    for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
+    pv_block(nkk - 1, std::true_type{});
+    const float i0 = 1.f / ol[0], i1 = 1.f / ol[2];
     const int r0 = row0 + g, r1 = row0 + g + 8;
     if (r0 < len) {
       bf16* op = ctx + (int64_t)(off + r0) * D + head * DH + 2 * t4;
