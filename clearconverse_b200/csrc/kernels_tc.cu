@@ -688,7 +688,8 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
          *hb = reinterpret_cast<bf16*>(hid);
     static const bool fused = !(getenv("RESEP_FUSED") && getenv("RESEP_FUSED")[0] == '0');
     if (fused) {
-      if ((rc = launch_qkv_tc(h, lw, o, qb, rows, st))) return rc;   // norm1 + in-projection in one kernel
+      static const bool qkv2 = !(getenv("RESEP_QKV2") && getenv("RESEP_QKV2")[0] == '0');
+      if ((rc = qkv2 ? launch_qkv2_tc(h, lw, o, qb, rows, st) : launch_qkv_tc(h, lw, o, qb, rows, st))) return rc;   // norm1 + in-projection in one kernel
     } else {
       if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
       if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;

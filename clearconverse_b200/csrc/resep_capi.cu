@@ -95,7 +95,7 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   Tf(d.fc_w_tf, d.fc_w_lo, w->fc_w, NSPK * D * D);
   d.pe_rows = w->pe_rows;
   const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
-  constexpr size_t POST_PAR = 4 * D + FFN;
+  constexpr size_t POST_PAR = 4 * D + FFN + 3 * D + 2 * D;
   h->host_par.assign(3 * NL * POST_PAR, 0.f);
   for (int b = 0; b < 3; ++b) {
     const ResepBlockWeights& sb = *src_blocks[b];
@@ -113,7 +113,10 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
         float* hp = h->host_par.data() + (size_t)(b * NL + l) * POST_PAR;
         std::memcpy(hp, s.out_proj_b, D * 4); std::memcpy(hp + D, s.norm2_w, D * 4); std::memcpy(hp + 2 * D, s.norm2_b, D * 4);
         std::memcpy(hp + 3 * D, s.ffn2_b, D * 4); std::memcpy(hp + 4 * D, s.ffn1_b, FFN * 4);
+        std::memcpy(hp + 4 * D + FFN, s.in_proj_b, 3 * D * 4);
+        std::memcpy(hp + 7 * D + FFN, s.norm1_w, D * 4); std::memcpy(hp + 8 * D + FFN, s.norm1_b, D * 4);
         t.h_post_par = hp;
+        t.h_in_b = hp + 4 * D + FFN;
       }
       F(t.norm1_w, s.norm1_w, D); F(t.norm1_b, s.norm1_b, D);
       F(t.in_w, s.in_proj_w, 3 * D * D); F(t.in_b, s.in_proj_b, 3 * D);

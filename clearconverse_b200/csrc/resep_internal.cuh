@@ -36,6 +36,7 @@ struct LayerDev {
   // HOST copy of out_b[128], norm2_w[128], norm2_b[128], f2_b[128], f1_b[1024]: k_post2_tc takes them as kernel
   // parameters (constant bank) so that its epilogues do not spend shared-memory bandwidth on broadcast loads
   const float* h_post_par;
+  const float* h_in_b;      // HOST copy of in_b[384], norm1_w[128], norm1_b[128] (k_qkv2_tc kernel parameters)
 };
 struct BlockDev {
   LayerDev layers[NL];
@@ -84,7 +85,7 @@ struct ResepHandle {
   int sm_count = 148;
   std::string err;
   void* arena = nullptr;  // all weights, one allocation
-  std::vector<float> host_par;   // per layer: the 1,536 floats LayerDev::h_post_par points at
+  std::vector<float> host_par;   // per layer: the 1,536 floats LayerDev::h_post_par points at + 384 for h_in_b
   size_t arena_bytes = 0;
   resep::WeightsDev w;
   std::vector<resep::Plan*> plans;

@@ -20,6 +20,9 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
 // Fused norm1 + in-projection (kernels_layer.cu), bf16 mode: qkv[rows,384] = LN1(o) . Win^T + bin
 int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st);
 
+// The same on CTA pairs with resident weights (kernels_qkv2.cu): the default; RESEP_QKV2=0 selects the 1-CTA kernel
+int launch_qkv2_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st);
+
 extern long long* g_post_trace;   // development aid: clock trace buffer of k_post_tc (null unless RESEP_TRACE is set)
 
 // output_fc: mask[M,256] = relu(prelu(a) . fc_w^T + fc_b)   (fp32 out)
