@@ -134,6 +134,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();                           // the next kernel's prologue may overlap this kernel's tail
   int tr_n = 0;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -161,6 +162,9 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Programmatic dependent launch: the weight ring is filled without waiting for the previous kernel (attention,
+  // which produces ctx); every other role touches ctx / o and waits for it to complete first.
+  if (warp != 0) pdl_wait();
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer (both CTAs: own halves)
     if (lane == 0 && n_iters > 0 && !(args.dbg & 1)) {
@@ -547,7 +551,7 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
   }
   const int ptiles = (int)((rows + 255) / 256);
   const int npairs = ptiles < max_pairs ? ptiles : max_pairs;
-  kern<<<2 * npairs, post2::THREADS, post2::SMEM, st>>>(tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L, a);
+  RESEP_CUDA(h, launch_pdl(kern, dim3(2 * npairs), dim3(post2::THREADS), post2::SMEM, st, tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L, a));
   RESEP_LAUNCH_CHECK(h, "k_post2_tc");
   return RESEP_OK;
 }

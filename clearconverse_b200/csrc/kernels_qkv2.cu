@@ -82,6 +82,7 @@ k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();                                   // the next kernel's prologue may overlap this kernel's tail
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -103,6 +104,9 @@ k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Programmatic dependent launch: everything above and the weight loads below are independent of the previous
+  // kernel (which produced `o` and may still be reading the qkv buffer this kernel overwrites).
+  if (warp != 0) pdl_wait();
   if (warp == 0) {
     if (lane == 0 && n_iters > 0) {                // resident weights: this CTA's 64 rows of every (n, part) tile
       const uint32_t wfull = mapa_u32(smem_u32(w_full), 0);
@@ -299,7 +303,7 @@ int launch_qkv2_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv
   const int max_pairs = h->sm_count / 2;
   const int ptiles = (int)((rows + 255) / 256);
   const int npairs = ptiles < max_pairs ? ptiles : max_pairs;
-  kern<<<2 * npairs, qkv2::THREADS, qkv2::SMEM, st>>>(tmO, tmW, tmWL, tmQ, a);
+  RESEP_CUDA(h, launch_pdl(kern, dim3(2 * npairs), dim3(qkv2::THREADS), qkv2::SMEM, st, tmO, tmW, tmWL, tmQ, a));
   RESEP_LAUNCH_CHECK(h, "k_qkv2_tc");
   return RESEP_OK;
 }

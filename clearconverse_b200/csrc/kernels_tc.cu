@@ -426,6 +426,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
                                                                  int seq_len, const int* __restrict__ seq_off) {
   __shared__ __align__(16) bf16 Ks[160 * AS_ROW];
   __shared__ __align__(16) bf16 Vs[160 * AS_ROW];
+  pdl_trigger();
+  pdl_wait();                                        // qkv comes from the previous kernel in the stream
   int off, len;
   if (seq_off != nullptr) {
     off = seq_off[blockIdx.x];
@@ -603,14 +605,14 @@ static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int
   if (tile_seq == nullptr) {
     if (n_seq == 0) return RESEP_OK;
     if (seq_len <= 160) {
-      k_attention_bf16_short<<<dim3((unsigned)n_seq, NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr);
+      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len, (const int*)nullptr));
     } else {
       const int tps = (seq_len + AKT - 1) / AKT;
       k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
     }
   } else if (max_len <= 160) {
     if (n_seq == 0) return RESEP_OK;
-    k_attention_bf16_short<<<dim3((unsigned)n_seq, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off);
+    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, 0, seq_off));
   } else {
     if (n_tiles128 == 0) return RESEP_OK;
     k_attention_bf16<<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);

@@ -139,6 +139,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// pdl_trigger: the next kernel in the stream (launched with the programmatic-stream-serialization attribute) may be
+// scheduled as soon as every CTA of this grid has executed it (or exited); pdl_wait: blocks until the previous
+// grid has completed and its memory is visible.  Everything before pdl_wait must be independent of that grid.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

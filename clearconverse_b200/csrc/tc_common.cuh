@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "ptx_sm100.cuh"
@@ -28,6 +29,20 @@ static int make_tmap(ResepHandle* h, CUtensorMap* m, const T* base, int64_t rows
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return RESEP_OK;
+}
+
+// Launch with programmatic dependent launch: the kernel may start while its predecessor in the stream drains; it
+// calls ptx::pdl_wait() before touching anything the predecessor produced.  RESEP_PDL=0 launches it serialised.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool pdl = !(getenv("RESEP_PDL") && getenv("RESEP_PDL")[0] == '0');
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 }  // namespace resep
