@@ -422,33 +422,42 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 // Per score: FMNMX (pass 1); FFMA + MUFU.EX2 + FADD + half a pack (pass 2) -- the MUFU unit (16/clk/SM)
 // is the floor.
 constexpr int AS_ROW = 24;   // halves per staged K / V row (16 used)
-__global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx,
-                                                                 int seq_len, const int* __restrict__ seq_off) {
-  __shared__ __align__(16) bf16 Ks[160 * AS_ROW];
-  __shared__ __align__(16) bf16 Vs[160 * AS_ROW];
+// Template: KMAX keys staged per (sequence, head) CTA, WARPS warps of MT m16 query tiles each (WARPS * MT * 16 query rows
+// per CTA; longer sequences take `q_tiles` CTAs).  <160, 5, 2> is the per-chunk kernel; <448, 4, 1> covers the coupled
+// memory transformer's single sequence of all chunk summaries (432 rows at config 2) with 7 x 8 CTAs instead of the
+// 3 x 8 of the streaming kernel below, which is latency-bound at that size.
+template <int KMAX, int WARPS, int MT>
+__global__ void __launch_bounds__(32 * WARPS, KMAX <= 160 ? 6 : 2)
+k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int seq_len, const int* __restrict__ seq_off,
+                       int q_tiles) {
+  constexpr int THREADS = 32 * WARPS, QROWS = WARPS * MT * 16;
+  __shared__ __align__(16) bf16 Ks[KMAX * AS_ROW];
+  __shared__ __align__(16) bf16 Vs[KMAX * AS_ROW];
   pdl_trigger();
   pdl_wait();                                        // qkv comes from the previous kernel in the stream
+  const int seq = blockIdx.x / q_tiles, q0 = (blockIdx.x % q_tiles) * QROWS;
   int off, len;
   if (seq_off != nullptr) {
-    off = seq_off[blockIdx.x];
-    len = seq_off[blockIdx.x + 1] - off;
+    off = seq_off[seq];
+    len = seq_off[seq + 1] - off;
   } else {
-    off = blockIdx.x * seq_len;
+    off = seq * seq_len;
     len = seq_len;
   }
+  if (q0 >= len) return;
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
-  __shared__ float s_kmax[5];
+  __shared__ float s_kmax[WARPS];
   // Q fragments of this warp's two m16 tiles, requested before the K / V rows so that the CTA pays one global-memory
   // latency, not three (rows past the sequence read as zero)
-  uint32_t qf[2][4];
+  uint32_t qf[MT][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      const int r = warp * 32 + mt * 16 + g + hh * 8;
+      const int r = q0 + warp * (16 * MT) + mt * 16 + g + hh * 8;
       uint32_t lo = 0, hi = 0;
       if (r < len) {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(qbase + (int64_t)r * (3 * D));
@@ -458,33 +467,39 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
       qf[mt][hh] = lo;
       qf[mt][hh + 2] = hi;
     }
-  {  // stage one key / value row per thread (rows past the sequence are zero); squared norm of the key row
-    const int key = threadIdx.x;
-    uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
-    if (key < len) {
-      const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
-      k0 = p[0]; k1 = p[1];
-      const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
-      v0 = pv[0]; v1 = pv[1];
-    }
-    uint4* kd = reinterpret_cast<uint4*>(Ks + key * AS_ROW);
-    uint4* vd = reinterpret_cast<uint4*>(Vs + key * AS_ROW);
-    kd[0] = k0; kd[1] = k1;
-    vd[0] = v0; vd[1] = v1;
-    const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-    float kn2 = 0.f;
+  {  // stage the key / value rows (rows past the sequence up to the next multiple of 16 are zero); max squared key norm
+    float kn2max = 0.f;
+    const int kp = (len + 15) & ~15;
+    for (int key = threadIdx.x; key < kp; key += THREADS) {
+      uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+      if (key < len) {
+        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
+        k0 = p[0]; k1 = p[1];
+        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
+        v0 = pv[0]; v1 = pv[1];
+      }
+      uint4* kd = reinterpret_cast<uint4*>(Ks + key * AS_ROW);
+      uint4* vd = reinterpret_cast<uint4*>(Vs + key * AS_ROW);
+      kd[0] = k0; kd[1] = k1;
+      vd[0] = v0; vd[1] = v1;
+      const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+      float kn2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
-      kn2 = fmaf(f.x, f.x, kn2);
-      kn2 = fmaf(f.y, f.y, kn2);
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
+        kn2 = fmaf(f.x, f.x, kn2);
+        kn2 = fmaf(f.y, f.y, kn2);
+      }
+      kn2max = fmaxf(kn2max, kn2);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
-    if (lane == 0) s_kmax[warp] = kn2;
+    for (int o = 16; o > 0; o >>= 1) kn2max = fmaxf(kn2max, __shfl_xor_sync(0xffffffffu, kn2max, o));
+    if (lane == 0) s_kmax[warp] = kn2max;
   }
   __syncthreads();
-  const float kmax2 = fmaxf(fmaxf(fmaxf(s_kmax[0], s_kmax[1]), fmaxf(s_kmax[2], s_kmax[3])), s_kmax[4]);
+  float kmax2 = s_kmax[0];
+#pragma unroll
+  for (int i = 1; i < WARPS; ++i) kmax2 = fmaxf(kmax2, s_kmax[i]);
   const int nkk = (len + 15) >> 4;                    // 16-key blocks holding at least one valid key
   constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
   // ldmatrix lane addressing: matrix m = lane / 8, row lane % 8
@@ -493,8 +508,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
   const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * AS_ROW + (lm >> 1) * 8;   // V^T: m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
   constexpr uint32_t ONES = 0x3F803F80u;              // bf16 (1.0, 1.0): B fragment of an all-ones [16 keys x 8] matrix
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int row0 = warp * 32 + mt * 16;
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row0 = q0 + warp * (16 * MT) + mt * 16;
     if (row0 >= len) break;                            // warp-uniform
     const uint32_t (&qa)[4] = qf[mt];
     // Softmax stabiliser.  Any m_i >= max_j s_ij gives the same softmax; by Cauchy-Schwarz s_ij <= |q_i| |k_j| so
@@ -598,21 +613,31 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_short(const bf16* __r
 
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
                                  const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st) {
-  ProfScope prof_scope(h, (tile_seq == nullptr ? seq_len : max_len) <= 160 ? "k_attention_bf16_short" : "k_attention_bf16", st);
+  const int longest = tile_seq == nullptr ? seq_len : max_len;
+  ProfScope prof_scope(h, longest <= 160 ? "k_attention_bf16_short" : longest <= 448 ? "k_attention_bf16_mid" : "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
   // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
   // of the next tile with identical results).
   if (tile_seq == nullptr) {
     if (n_seq == 0) return RESEP_OK;
     if (seq_len <= 160) {
-      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len, (const int*)nullptr));
+      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<160, 5, 2>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len,
+                               (const int*)nullptr, 1));
+    } else if (seq_len <= 448) {
+      const int qt = (seq_len + 63) / 64;
+      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<448, 4, 1>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, seq_len,
+                               (const int*)nullptr, qt));
     } else {
       const int tps = (seq_len + AKT - 1) / AKT;
       k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
     }
   } else if (max_len <= 160) {
     if (n_seq == 0) return RESEP_OK;
-    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, 0, seq_off));
+    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<160, 5, 2>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, 0, seq_off, 1));
+  } else if (max_len <= 448) {
+    if (n_seq == 0) return RESEP_OK;
+    const int qt = (max_len + 63) / 64;
+    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<448, 4, 1>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, 0, seq_off, qt));
   } else {
     if (n_tiles128 == 0) return RESEP_OK;
     k_attention_bf16<<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
