@@ -312,8 +312,18 @@ def main():
             achieved = work * reps / rec["launches"] / (avg_ms / 1e3) / 1e9
         else:
             peak = unit = achieved = None
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture, averaged per launch
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f).get(name.split("<")[0])
+            if tj:
+                L, S, chunks, M, _ = shapes(BATCH, T)
+                big, small = 16, rec["launches"] / reps - 16          # intra-block launches (M rows) and memory-block launches (chunks rows)
+                traffic = tj["dram_bytes_big_launch"] * (big + small * chunks / M) / (big + small)
+        except Exception:
+            traffic = None
         roofline = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": pk["_src"] + (" (sustained bf16: kernel timed inside the step)" if bound == "tensor" else ""),
                     "avg_launch_us": 1e3 * avg_ms, "launches_per_step": rec["launches"] / reps,
                     "share_of_step": rec["ms"] / sum(r["ms"] for r in prof.values()),
