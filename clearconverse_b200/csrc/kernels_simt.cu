@@ -383,14 +383,15 @@ int launch_attention_f32(ResepHandle* h, const float* qkv, float* ctx, int n_seq
 // to o; gLN statistics over all len*128 values of the sequence (fp64 accumulation of sum and
 // sum of squares); out = gln_w * (y - mu) * rstd + gln_b + xin; optional mean over the rows
 // (the chunk summary `output.mean(1)`).  `out` may alias `xin`.
-__global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* __restrict__ fn_w,
+template <int NWARP>
+__global__ void __launch_bounds__(32 * NWARP) k_block_epilogue(float* o, const float* __restrict__ fn_w,
                                                         const float* __restrict__ fn_b, const float* __restrict__ gln_w,
                                                         const float* __restrict__ gln_b, const float* xin, float* out,
                                                         float* __restrict__ seq_mean, int seq_len,
                                                         const int* __restrict__ seq_off) {
-  __shared__ double red[2][8];
+  __shared__ double red[2][NWARP];
   __shared__ float stat[2];
-  __shared__ __align__(16) float colsum[8][D];
+  __shared__ __align__(16) float colsum[NWARP][D];
   const int seq = blockIdx.x;
   int off, len;
   if (seq_off != nullptr) {
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 w4 = reinterpret_cast<const float4*>(fn_w)[lane], b4 = reinterpret_cast<const float4*>(fn_b)[lane];
   double s1 = 0.0, s2 = 0.0;
-  for (int r = warp; r < len; r += 8) {
+  for (int r = warp; r < len; r += NWARP) {
     float* row = o + (int64_t)(off + r) * D;
     float4 y = ln_row(reinterpret_cast<const float4*>(row)[lane], w4, b4);
     reinterpret_cast<float4*>(row)[lane] = y;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* _
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    for (int i = 0; i < NWARP; ++i) { a += red[0][i]; b += red[1][i]; }
     const double n = (double)len * D;
     const double mu = a / n;
     double var = b / n - mu * mu;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* _
   const float mu = stat[0], rstd = stat[1];
   const float4 g4 = reinterpret_cast<const float4*>(gln_w)[lane], h4 = reinterpret_cast<const float4*>(gln_b)[lane];
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = warp; r < len; r += 8) {
+  for (int r = warp; r < len; r += NWARP) {
     const int64_t idx = (int64_t)(off + r) * (D / 4) + lane;
     float4 y = reinterpret_cast<const float4*>(o)[idx];
     float4 x = reinterpret_cast<const float4*>(xin)[idx];
@@ -446,19 +447,112 @@ __global__ void __launch_bounds__(256) k_block_epilogue(float* o, const float* _
     if (threadIdx.x < D) {
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t += colsum[i][threadIdx.x];
+      for (int i = 0; i < NWARP; ++i) t += colsum[i][threadIdx.x];
       seq_mean[(int64_t)seq * D + threadIdx.x] = t / (float)len;
+    }
+  }
+}
+
+// Same, for equal-length sequences of at most 150 rows (every intra-chunk block): the LayerNorm'ed chunk stays in
+// shared memory between the statistics pass and the normalisation pass (76.8 KB, two CTAs per SM), so the kernel
+// moves 3 x 512 B per row (o in, xin in, out) instead of 5 x.  Optionally also writes PReLU(out) in bf16 -- the A
+// operand of the output_fc GEMM (resepformer.py `output_fc = Sequential(PReLU(), Conv1d(.., 1))`) -- saving the
+// separate PReLU kernel's pass over the activations.
+constexpr int EPI_T = 512;
+__global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* __restrict__ o, const float* __restrict__ fn_w,
+                                                                   const float* __restrict__ fn_b, const float* __restrict__ gln_w,
+                                                                   const float* __restrict__ gln_b, const float* xin, float* out,
+                                                                   float* __restrict__ seq_mean, int seq_len,
+                                                                   bf16* __restrict__ prelu_out, const float* __restrict__ prelu_a) {
+  extern __shared__ __align__(16) float ys[];            // [seq_len][128]
+  __shared__ double red[2][EPI_T / 32];
+  __shared__ float stat[2];
+  __shared__ __align__(16) float colsum[EPI_T / 32][D];
+  constexpr int NW_ = EPI_T / 32;
+  const int seq = blockIdx.x;
+  const int64_t off = (int64_t)seq * seq_len;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 w4 = reinterpret_cast<const float4*>(fn_w)[lane], b4 = reinterpret_cast<const float4*>(fn_b)[lane];
+  double s1 = 0.0, s2 = 0.0;
+  for (int r = warp; r < seq_len; r += NW_) {
+    float4 y = ln_row(reinterpret_cast<const float4*>(o + (off + r) * D)[lane], w4, b4);
+    reinterpret_cast<float4*>(ys + r * D)[lane] = y;
+    s1 += (double)y.x + (double)y.y + (double)y.z + (double)y.w;
+    s2 += (double)y.x * y.x + (double)y.y * y.y + (double)y.z * y.z + (double)y.w * y.w;
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < NW_; ++i) { a += red[0][i]; b += red[1][i]; }
+    const double n = (double)seq_len * D;
+    const double mu = a / n;
+    double var = b / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mu;
+    stat[1] = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+  }
+  __syncthreads();
+  const float mu = stat[0], rstd = stat[1];
+  const float4 g4 = reinterpret_cast<const float4*>(gln_w)[lane], h4 = reinterpret_cast<const float4*>(gln_b)[lane];
+  const float slope = prelu_out != nullptr ? prelu_a[0] : 0.f;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = warp; r < seq_len; r += NW_) {
+    const int64_t idx = (off + r) * (D / 4) + lane;
+    const float4 y = reinterpret_cast<const float4*>(ys + r * D)[lane];
+    const float4 x = reinterpret_cast<const float4*>(xin)[idx];
+    float4 v;
+    v.x = g4.x * (y.x - mu) * rstd + h4.x + x.x;
+    v.y = g4.y * (y.y - mu) * rstd + h4.y + x.y;
+    v.z = g4.z * (y.z - mu) * rstd + h4.z + x.z;
+    v.w = g4.w * (y.w - mu) * rstd + h4.w + x.w;
+    reinterpret_cast<float4*>(out)[idx] = v;
+    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+    if (prelu_out != nullptr) {
+      float4 pz;
+      pz.x = v.x >= 0.f ? v.x : slope * v.x; pz.y = v.y >= 0.f ? v.y : slope * v.y;
+      pz.z = v.z >= 0.f ? v.z : slope * v.z; pz.w = v.w >= 0.f ? v.w : slope * v.w;
+      store4(prelu_out + idx * 4, pz);
+    }
+  }
+  if (seq_mean != nullptr) {
+    *reinterpret_cast<float4*>(&colsum[warp][lane * 4]) = cs;
+    __syncthreads();
+    if (threadIdx.x < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < NW_; ++i) t += colsum[i][threadIdx.x];
+      seq_mean[(int64_t)seq * D + threadIdx.x] = t / (float)seq_len;
     }
   }
 }
 
 int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const float* fn_b, const float* gln_w,
                           const float* gln_b, const float* xin, float* out, float* seq_mean, int n_seq, int seq_len,
-                          const int* seq_off, cudaStream_t st) {
+                          const int* seq_off, cudaStream_t st, bf16* prelu_out, const float* prelu_a) {
   if (n_seq == 0) return RESEP_OK;
   ProfScope prof_scope_451(h, "k_block_epilogue", st);
-  k_block_epilogue<<<(unsigned)n_seq, 256, 0, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, seq_off);
+  if (seq_off == nullptr && seq_len <= CHUNK) {
+    const size_t smem = (size_t)seq_len * D * sizeof(float);
+    RESEP_CUDA(h, cudaFuncSetAttribute(k_block_epilogue_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, CHUNK * D * (int)sizeof(float)));
+    k_block_epilogue_chunk<<<(unsigned)n_seq, EPI_T, smem, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, prelu_out, prelu_a);
+    RESEP_LAUNCH_CHECK(h, "k_block_epilogue_chunk");
+    return RESEP_OK;
+  }
+  // few long sequences (the coupled memory transformer is ONE sequence of all chunk summaries): 32 warps per CTA
+  if (n_seq < 2 * h->sm_count)
+    k_block_epilogue<32><<<(unsigned)n_seq, 1024, 0, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, seq_off);
+  else
+    k_block_epilogue<8><<<(unsigned)n_seq, 256, 0, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, seq_off);
   RESEP_LAUNCH_CHECK(h, "k_block_epilogue");
+  if (prelu_out != nullptr) {   // long sequences: PReLU as its own pass
+    int64_t rows = 0;
+    if (seq_off == nullptr) rows = (int64_t)n_seq * seq_len;
+    else return set_err(h, RESEP_EINVAL, "block epilogue: fused PReLU needs equal-length sequences");
+    return launch_prelu_t<bf16>(h, out, prelu_a, prelu_out, rows * D, st);
+  }
   return RESEP_OK;
 }
 
@@ -477,6 +571,8 @@ __global__ void k_prelu(const float* __restrict__ x, const float* __restrict__ a
   store4(y + i * 4, v);
 }
 
+template <typename OutT>
+int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st);
 template <typename OutT>
 int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st) {
   int64_t n4 = n / 4;
@@ -498,43 +594,57 @@ int launch_prelu(ResepHandle* h, const float* x, const float* a, float* y, int64
 // the CTA stages h[l][s][n] = mask[row_l][2n+s] * x0[row_l][n] for frames q0-1 .. q0+31 in shared
 // memory, forms the 33 x 2 x 16 frame products against dec_w, and writes est[t][0..1] as float2.
 // Samples past T_est get no contribution and come out as exact zeros (upstream's F.pad).
-constexpr int DEC_SLOTS = 32;
+constexpr int DEC_SLOTS = 31;                       // 32 frames -> 64 (frame, speaker) rows x 4 tap quads = 256 threads
+constexpr int DEC_ROWS = (DEC_SLOTS + 1) * NSPK;   // 64 (frame, speaker) rows of the frame-product GEMM
+constexpr int DEC_HP = DEC_ROWS + 1;               // pitch of the transposed h tile (odd: conflict-free column writes)
 __global__ void __launch_bounds__(256) k_decoder(const float* __restrict__ mask, const float* __restrict__ x0,
                                                  const float* __restrict__ dec_w, const int64_t* __restrict__ item_off,
                                                  const int64_t* __restrict__ item_len, const int* __restrict__ item_L,
                                                  const int* __restrict__ item_row0, const int* __restrict__ tile_item,
                                                  const int* __restrict__ tile_slot0, float* __restrict__ est) {
+  // fr[(j, s)][k] = sum_n h[(j, s)][n] * dec_w[n][k] is a [66 x 128] . [128 x 16] product.  h is staged transposed
+  // (hs[n][row]) so that the 8 rows a warp works on are adjacent words, and each thread owns a 1 x 4 block of fr:
+  // one LDS.32 + one LDS.128 per 4 FMAs.
   extern __shared__ __align__(16) float dsm[];
-  float* hs = dsm;                                   // [33][2][128]
-  float* ws = hs + (DEC_SLOTS + 1) * NSPK * D;       // [128][16]
-  float* fr = ws + D * KSZ;                          // [33][2][16]
+  float* hs = dsm;                                   // [128][DEC_HP]
+  float* ws = hs + D * DEC_HP;                       // [128][16]
+  float* fr = ws + D * KSZ;                          // [66][16]
   const int item = tile_item[blockIdx.x];
   const int q0 = tile_slot0[blockIdx.x];
   const int L = item_L[item];
   const int64_t T = item_len[item];
   const int64_t row0 = item_row0[item];
-  for (int i = threadIdx.x; i < D * KSZ; i += 256) ws[i] = dec_w[i];
-  for (int i = threadIdx.x; i < (DEC_SLOTS + 1) * D; i += 256) {
-    const int j = i / D, n = i % D;
-    const int l = q0 - 1 + j;
-    float h0 = 0.f, h1 = 0.f;
-    if (l >= 0 && l < L) {
-      const float xv = x0[(row0 + l) * D + n];
-      const float2 mk = *reinterpret_cast<const float2*>(mask + (row0 + l) * (NSPK * D) + 2 * n);
-      h0 = mk.x * xv;
-      h1 = mk.y * xv;
+  for (int i = threadIdx.x; i < D * KSZ / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = reinterpret_cast<const float4*>(dec_w)[i];
+  {  // 32 frames x 128 filters = 16 (frame, filter) pairs per thread: all loads issued before any is used
+    const int n = threadIdx.x & (D - 1), jb = threadIdx.x >> 7;       // frames jb, jb + 2, ..., jb + 30
+    float xv[16];
+    float2 mk[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int l = q0 - 1 + jb + 2 * u;
+      const bool ok = l >= 0 && l < L;
+      xv[u] = ok ? __ldg(x0 + (row0 + l) * D + n) : 0.f;
+      mk[u] = ok ? __ldg(reinterpret_cast<const float2*>(mask + (row0 + l) * (NSPK * D) + 2 * n)) : make_float2(0.f, 0.f);
     }
-    hs[(j * NSPK + 0) * D + n] = h0;
-    hs[(j * NSPK + 1) * D + n] = h1;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = jb + 2 * u;
+      hs[n * DEC_HP + 2 * j] = mk[u].x * xv[u];
+      hs[n * DEC_HP + 2 * j + 1] = mk[u].y * xv[u];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (DEC_SLOTS + 1) * NSPK * KSZ; i += 256) {
-    const int k = i % KSZ, js = i / KSZ;
-    const float* hp = hs + js * D;
-    float acc = 0.f;
+  {
+    const int kq = threadIdx.x & 3, row = threadIdx.x >> 2;          // 64 rows x 4 tap quads
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-    for (int n = 0; n < D; ++n) acc = fmaf(hp[n], ws[n * KSZ + k], acc);
-    fr[i] = acc;
+    for (int n = 0; n < D; ++n) {
+      const float hv = hs[n * DEC_HP + row];
+      const float4 w4 = *reinterpret_cast<const float4*>(ws + n * KSZ + 4 * kq);
+      acc.x = fmaf(hv, w4.x, acc.x); acc.y = fmaf(hv, w4.y, acc.y);
+      acc.z = fmaf(hv, w4.z, acc.z); acc.w = fmaf(hv, w4.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(fr + row * KSZ + 4 * kq) = acc;
   }
   __syncthreads();
   float* dst = est + 2 * item_off[item];
@@ -552,8 +662,8 @@ __global__ void __launch_bounds__(256) k_decoder(const float* __restrict__ mask,
 
 int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Plan& p, float* est, cudaStream_t st) {
   if (p.n_dec_tiles == 0) return RESEP_OK;
-  const size_t smem = ((DEC_SLOTS + 1) * NSPK * D + D * KSZ + (DEC_SLOTS + 1) * NSPK * KSZ) * sizeof(float);
-  static_assert(((DEC_SLOTS + 1) * NSPK * D + D * KSZ + (DEC_SLOTS + 1) * NSPK * KSZ) * sizeof(float) <= 48 * 1024, "decoder smem");
+  const size_t smem = (D * DEC_HP + D * KSZ + DEC_ROWS * KSZ) * sizeof(float);
+  static_assert((D * DEC_HP + D * KSZ + DEC_ROWS * KSZ) * sizeof(float) <= 48 * 1024, "decoder smem");
   ProfScope prof_scope_547(h, "k_decoder", st);
   k_decoder<<<(unsigned)p.n_dec_tiles, 256, smem, st>>>(mask, x0, h->w.dec_w, p.d_item_off, p.d_item_len, p.d_item_L,
                                                        p.d_item_row0, p.d_dec_tile_item, p.d_dec_tile_slot0, est);

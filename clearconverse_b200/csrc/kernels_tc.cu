@@ -744,11 +744,11 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
 }
 
 int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, int64_t M, int precision,
-                cudaStream_t st) {
+                cudaStream_t st, bool prelu_done) {
   int rc;
   if (precision == RESEP_PREC_BF16) {
     bf16* yb = reinterpret_cast<bf16*>(y_scratch);
-    if ((rc = launch_prelu_t<bf16>(h, a, h->w.prelu_a, yb, M * D, st))) return rc;
+    if (!prelu_done && (rc = launch_prelu_t<bf16>(h, a, h->w.prelu_a, yb, M * D, st))) return rc;
     return gemm_bf16<EPI_STORE_F32>(h, h->w16_mode, yb, h->w.fc_w_bf, h->w.fc_w_bl, h->w.fc_b, mask, M, NSPK * D, D,
                                    true, st);
   }

@@ -216,7 +216,7 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
   std::vector<int> dec_tile_item, dec_tile_slot0;
   for (int i = 0; i < B; ++i) {
     const int64_t slots = (item_len[i] + STRIDE - 1) / STRIDE;
-    for (int64_t q = 0; q < slots; q += 32) { dec_tile_item.push_back(i); dec_tile_slot0.push_back((int)q); }
+    for (int64_t q = 0; q < slots; q += 31) { dec_tile_item.push_back(i); dec_tile_slot0.push_back((int)q); }   // DEC_SLOTS of k_decoder
   }
   p->n_dec_tiles = (int)dec_tile_item.size();
 
@@ -330,14 +330,15 @@ static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc
 }
 
 static int run_block(ResepHandle* h, int blk, const float* xprev, const float* hc, float* xin, float* o, float* out,
-                     float* seq_mean, const SeqDesc& sd, const Workspace& ws, int precision, cudaStream_t st) {
+                     float* seq_mean, const SeqDesc& sd, const Workspace& ws, int precision, cudaStream_t st,
+                     bf16* prelu_out = nullptr) {
   int rc;
   const BlockDev& bw = h->w.blk[blk];
   if ((rc = launch_block_prologue(h, xprev, hc, xin, o, sd.rows, sd.pos, sd.seq_len, st))) return rc;
   for (int l = 0; l < NL; ++l)
     if ((rc = run_layer(h, bw.layers[l], o, sd, ws, precision, st))) return rc;
   return launch_block_epilogue(h, o, bw.fn_w, bw.fn_b, bw.gln_w, bw.gln_b, xin, out, seq_mean, sd.n_seq, sd.seq_len,
-                               sd.seq_off, st);
+                               sd.seq_off, st, prelu_out, h->w.prelu_a);
 }
 
 static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
@@ -377,7 +378,9 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
   if (dbg && dbg->mem0)
     RESEP_CUDA(h, cudaMemcpyAsync(dbg->mem0, ws.hc_out, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // seg_model[1](out + hc)
-  if ((rc = run_block(h, 1, ws.a, ws.hc_out, ws.a, ws.o, ws.a, nullptr, intra, ws, precision, st))) return rc;
+  // in the bf16 mode the block epilogue also emits PReLU(out) in bf16 (ws.y), the A operand of output_fc
+  bf16* prelu_out = precision == RESEP_PREC_BF16 ? reinterpret_cast<bf16*>(ws.y) : nullptr;
+  if ((rc = run_block(h, 1, ws.a, ws.hc_out, ws.a, ws.o, ws.a, nullptr, intra, ws, precision, st, prelu_out))) return rc;
   if (dbg && dbg->seg1) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg1, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // output_fc (PReLU -> 1x1 conv 128->256) -> ReLU mask -> x encoder features -> decoder
@@ -386,7 +389,7 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
     if ((rc = launch_prelu(h, ws.a, h->w.prelu_a, ws.y, p->M * D, st))) return rc;
     if ((rc = launch_gemm_f32(h, ws.y, h->w.fc_w, h->w.fc_b, nullptr, mask, p->M, NSPK * D, D, true, st))) return rc;
   } else {
-    if ((rc = tc_run_mask(h, ws.a, ws.y, mask, p->M, precision, st))) return rc;
+    if ((rc = tc_run_mask(h, ws.a, ws.y, mask, p->M, precision, st, prelu_out != nullptr))) return rc;
   }
   return launch_decoder(h, mask, ws.x0, *p, est, st);
 }

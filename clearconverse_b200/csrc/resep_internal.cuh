@@ -152,9 +152,10 @@ int launch_gemm_f32(ResepHandle* h, const float* A, const float* W, const float*
 int launch_attention_f32(ResepHandle* h, const float* qkv, float* ctx, int n_seq, int seq_len, const int* seq_off,
                          const int* tile_seq, const int* tile_q0, int n_tiles, cudaStream_t st);
 // final LayerNorm + gLN per sequence + skip (+ per-sequence column mean)
+// prelu_out (optional, bf16 [rows,128]): additionally PReLU(out; prelu_a) for the output_fc GEMM
 int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const float* fn_b, const float* gln_w,
                           const float* gln_b, const float* xin, float* out, float* seq_mean, int n_seq, int seq_len,
-                          const int* seq_off, cudaStream_t st);
+                          const int* seq_off, cudaStream_t st, bf16* prelu_out = nullptr, const float* prelu_a = nullptr);
 // y = round_to_tf32(LayerNorm(x)); x[i] = round_to_tf32(x[i]) in place
 int launch_layernorm_tf32(ResepHandle* h, const float* x, const float* w, const float* b, float* y, int64_t rows,
                           cudaStream_t st);

@@ -26,7 +26,9 @@ int launch_qkv2_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv
 extern long long* g_post_trace;   // development aid: clock trace buffer of k_post_tc (null unless RESEP_TRACE is set)
 
 // output_fc: mask[M,256] = relu(prelu(a) . fc_w^T + fc_b)   (fp32 out)
-int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, int64_t M, int precision, cudaStream_t st);
+// prelu_done: y_scratch already holds PReLU(a) in bf16 (written by the block epilogue)
+int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, int64_t M, int precision, cudaStream_t st,
+                bool prelu_done = false);
 
 // out = A . W^T + bias for arbitrary DEVICE fp32 W (test hook for the GEMM kernel)
 int tc_linear_test(ResepHandle* h, const float* A, const float* W, const float* bias, float* out, int64_t M, int N, int K,

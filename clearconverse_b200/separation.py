@@ -299,6 +299,51 @@ class SepformerSeparation:
             torch.cat(flat), offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT)
         return [est[2 * o:2 * (o + n)].view(n, NUM_SPKS) for o, n in zip(offs, lens)]
 
+    @torch.no_grad()
+    def separate_stream(self, batches, out_buffers=None, depth: int = 2):
+        """Pipelined driver for a sequence of HOST batches (the batched overlap driver of SURVEY.md section 8f-1):
+        yields, in order, a pinned HOST tensor [B,T,n_spk] per input batch.  The host->device copy of batch i+1 and
+        the device->host copy of batch i-1 run on their own streams under the kernels of batch i, so the copies cost
+        no throughput.  ``batches``: iterable of [B,T] float32 CPU tensors (pinned for truly asynchronous copies);
+        ``out_buffers``: optional list of >= ``depth`` pinned [B,T,n_spk] tensors to reuse (a yielded tensor is
+        overwritten ``depth`` batches later)."""
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        inflight = []                                     # (event, host_out)
+
+        def drain_one():
+            ev, out = inflight.pop(0)
+            ev.synchronize()
+            return out
+
+        for i, mix in enumerate(batches):
+            self._check_mix(mix)
+            B, T = mix.shape
+            with torch.cuda.stream(h2d):
+                dmix = mix.to(dev, non_blocking=True)
+                up = torch.cuda.Event(); up.record(h2d)
+            compute.wait_event(up)
+            dmix.record_stream(compute)
+            est = torch.ops.clearconverse_b200.resep_separate(
+                dmix.view(-1), [b * T for b in range(B)], [T] * B, self._engine.id,
+                _lib.PRECISIONS[self.precision], _lib.BATCH_MODES[self.batch_mode]).view(B, T, NUM_SPKS)
+            done = torch.cuda.Event(); done.record(compute)
+            if out_buffers is not None:
+                host = out_buffers[i % len(out_buffers)]
+            else:
+                host = torch.empty(B, T, NUM_SPKS, dtype=torch.float32).pin_memory()
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                host.copy_(est, non_blocking=True)
+                est.record_stream(d2h)
+                down = torch.cuda.Event(); down.record(d2h)
+            inflight.append((down, host))
+            if len(inflight) >= depth:
+                yield drain_one()
+        while inflight:
+            yield drain_one()
+
     def separate_batch_debug(self, mix: torch.Tensor) -> tuple[torch.Tensor, dict]:
         """separate_batch + intermediates (encoder / block outputs) for per-kernel parity tests."""
         self._check_mix(mix)

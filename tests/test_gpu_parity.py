@@ -274,3 +274,12 @@ def test_independent_mode_is_batch_composition_invariant(make_sep):
     alone = [sep.separate_segments([s])[0] for s in segs]
     for a, b, c in zip(all_at_once, rev, alone):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_separate_stream_equals_separate_batch(sep_fp32):
+    """The pipelined host-batch driver (copies overlapped with compute) returns what separate_batch returns."""
+    batches = [synth_batch(2, 4000, 40 + i).pin_memory() for i in range(5)]
+    outs = [o.clone() for o in sep_fp32.separate_stream(iter(batches))]
+    assert len(outs) == 5
+    for b, o in zip(batches, outs):
+        assert torch.equal(o, sep_fp32.separate_batch(b).cpu())
