@@ -152,6 +152,11 @@ static void free_plan(Plan* p) {
   delete p;
 }
 
+static void drop_graphs_of(ResepHandle* h) {
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_t* item_len, int batch_mode,
                     cudaStream_t st, Plan** out) {
   std::vector<int64_t> key;
@@ -260,6 +265,7 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
   p->d_dec_tile_slot0 = reinterpret_cast<const int*>(base + o_dts);
   p->last_use = h->tick;
   if (h->plans.size() >= 16) {   // evict the least recently used plan (stream-ordered free is safe: cudaFree syncs)
+    drop_graphs_of(h);             // captured graphs hold pointers into plan tables
     auto it = std::min_element(h->plans.begin(), h->plans.end(),
                                [](const Plan* a, const Plan* b) { return a->last_use < b->last_use; });
     free_plan(*it);
@@ -341,9 +347,82 @@ static int run_block(ResepHandle* h, int blk, const float* xprev, const float* h
                                sd.seq_off, st, prelu_out, h->w.prelu_a);
 }
 
+static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
+                         float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
+                         cudaStream_t st, const ResepDebugOut* dbg);
+
+static void drop_graphs(ResepHandle* h) {
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+// Forward pass, replayed from a CUDA graph when the same (shapes, buffers, mode) has been seen before.
 static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
                         float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                         cudaStream_t st, const ResepDebugOut* dbg) {
+  if (!h) return RESEP_EINVAL;
+  if (dbg != nullptr || h->prof_on || !h->use_graphs || precision != RESEP_PREC_BF16 || !mix || !item_off || !item_len || !est || B <= 0)
+    return forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, dbg);
+  std::vector<uint64_t> key;
+  key.reserve(6 + 2 * (size_t)B);
+  key.push_back((uint64_t)(uintptr_t)mix); key.push_back((uint64_t)(uintptr_t)est); key.push_back((uint64_t)(uintptr_t)workspace);
+  key.push_back((uint64_t)workspace_bytes); key.push_back((uint64_t)precision * 16 + (uint64_t)batch_mode); key.push_back((uint64_t)B);
+  for (int i = 0; i < B; ++i) { key.push_back((uint64_t)item_off[i]); key.push_back((uint64_t)item_len[i]); }
+  h->tick++;
+  ResepHandle::GraphRec* rec = nullptr;
+  for (auto& g : h->graphs) if (g.key == key) { rec = &g; break; }
+  if (rec && rec->exec) {
+    rec->last_use = h->tick;
+    RESEP_CUDA(h, cudaSetDevice(h->device));
+    RESEP_CUDA(h, cudaGraphLaunch(rec->exec, st));
+    h->launches += rec->launches;
+    return RESEP_OK;
+  }
+  if (!rec) {   // first sighting: run eagerly and remember the key
+    int rc = forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, nullptr);
+    if (rc) return rc;
+    if (h->graphs.size() >= 12) {
+      auto it = std::min_element(h->graphs.begin(), h->graphs.end(), [](const ResepHandle::GraphRec& a, const ResepHandle::GraphRec& b) { return a.last_use < b.last_use; });
+      if (it->exec) cudaGraphExecDestroy(it->exec);
+      h->graphs.erase(it);
+    }
+    ResepHandle::GraphRec g;
+    g.key = key; g.last_use = h->tick;
+    h->graphs.push_back(g);
+    return RESEP_OK;
+  }
+  // second sighting: capture on the handle's own stream, instantiate, launch on the caller's stream
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  if (!h->cap_stream) RESEP_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  const int64_t l0 = h->launches;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+  int rc = RESEP_OK;
+  if (e == cudaSuccess) {
+    rc = forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, h->cap_stream, nullptr);
+    e = cudaStreamEndCapture(h->cap_stream, &graph);
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess && rc == RESEP_OK && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess || rc != RESEP_OK || !exec) {   // capture failed: run eagerly; give up on graphs after three failures
+    cudaGetLastError();
+    h->launches = l0;
+    static int failures = 0;
+    if (++failures >= 3) h->use_graphs = 0;
+    drop_graphs(h);
+    return forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, nullptr);
+  }
+  rec->exec = exec;
+  rec->launches = h->launches - l0;
+  rec->last_use = h->tick;
+  RESEP_CUDA(h, cudaGraphLaunch(exec, st));
+  return RESEP_OK;
+}
+
+static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
+                         float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
+                         cudaStream_t st, const ResepDebugOut* dbg) {
   if (!h) return RESEP_EINVAL;
   if (!mix || !item_off || !item_len || !est || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or B <= 0");
   if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
@@ -431,6 +510,7 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
     else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;   // every weight as hi + lo
     else if (!strcmp(m, "mixed")) h->w16_mode = 2;    // default
   }
+  if (const char* g = getenv("RESEP_GRAPH")) h->use_graphs = g[0] != '0';
   int rc = upload_weights(h, w);
   if (rc) {
     g_create_err = h->err;
@@ -446,6 +526,7 @@ int resep_load_weights(ResepHandle* h, const ResepWeights* w) {
   if (!h) return RESEP_EINVAL;
   RESEP_CUDA(h, cudaSetDevice(h->device));
   RESEP_CUDA(h, cudaDeviceSynchronize());
+  drop_graphs_of(h);   // graphs bake in the kernel parameters (biases are passed by value) of the old weights
   int rc = upload_weights(h, w);
   if (rc) return rc;
   tc_destroy(h);   // packed tensor-core copies are rebuilt lazily from the new weights
@@ -458,6 +539,8 @@ int resep_destroy(ResepHandle* h) {
   cudaDeviceSynchronize();
   tc_destroy(h);
   resep_profile(h, 0);
+  drop_graphs_of(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (Plan* p : h->plans) free_plan(p);
   if (h->arena) cudaFree(h->arena);
   delete h;

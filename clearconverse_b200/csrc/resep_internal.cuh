@@ -97,6 +97,18 @@ struct ResepHandle {
   bool prof_on = false;   // resep_profile(): bracket every launch with CUDA events
   struct ProfRec { cudaEvent_t a, b; const char* name; };
   std::vector<ProfRec> prof;
+  // CUDA graphs of whole forward passes, keyed by (plan, buffers, mode): the ~80 launches of a forward cost more
+  // host time than the kernels take on the device at small batch sizes (api.py calls with B = 1)
+  struct GraphRec {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    uint64_t last_use = 0;
+    bool seen_only = true;   // first sighting runs eagerly (plans, attributes and occupancy queries are set up outside capture)
+  };
+  std::vector<GraphRec> graphs;
+  cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy default stream)
+  int use_graphs = 1;                  // RESEP_GRAPH=0 disables
   bool tc_ready = false;  // tensor maps for the tcgen05 path built
   void* tc_state = nullptr;
 };

@@ -53,6 +53,7 @@ class _Engine:
         rc = self.lib.resep_create(C.byref(cfg), C.byref(self.packed.struct), self.device.index, C.byref(self.handle))
         _lib.check(self.lib, None, rc)
         self.workspace = None
+        self._static_io: dict = {}        # (offs, lens, slot) -> (mix_buf, est_buf): fixed addresses let the C side replay a CUDA graph
         with _ENGINES_LOCK:
             self.id = _NEXT_ID[0]
             _NEXT_ID[0] += 1
@@ -74,17 +75,35 @@ class _Engine:
             self.workspace = torch.empty(int(need.value * 1.0) + 1024, dtype=torch.uint8, device=self.device)
         return self.workspace
 
+    def static_io(self, offs, lens, total: int, slot: int = 0):
+        """Persistent (mix, est) device buffers for one batch shape.  The C ABI keys its CUDA graphs on buffer
+        addresses, so feeding the same buffers makes every call after the second a single graph launch."""
+        key = (tuple(offs), tuple(lens), total, slot)
+        io = self._static_io.get(key)
+        if io is None:
+            if len(self._static_io) >= 24:
+                self._static_io.pop(next(iter(self._static_io)))
+            with torch.cuda.device(self.device):
+                io = (torch.empty(total, dtype=torch.float32, device=self.device),
+                      torch.zeros(2 * total, dtype=torch.float32, device=self.device))
+            self._static_io[key] = io
+        return io
+
     def forward(self, mix_flat: torch.Tensor, offs: list[int], lens: list[int], precision: int, batch_mode: int,
-                debug: dict | None = None) -> torch.Tensor:
-        """mix_flat: 1-D fp32 CUDA tensor holding every item; returns est_flat [2 * mix_flat.numel()]."""
+                debug: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """mix_flat: 1-D fp32 CUDA tensor holding every item; returns est_flat [2 * mix_flat.numel()]
+        (``out`` if given: it must be zero-filled where items leave gaps)."""
         B = len(lens)
         c_off = (C.c_int64 * B)(*offs)
         c_len = (C.c_int64 * B)(*lens)
         with torch.cuda.device(self.device):
             ws = self._workspace_for(c_len, B, precision)
-            est = torch.zeros(2 * mix_flat.numel(), dtype=torch.float32, device=self.device) \
-                if _needs_zero_fill(offs, lens, mix_flat.numel()) else \
-                torch.empty(2 * mix_flat.numel(), dtype=torch.float32, device=self.device)
+            if out is not None:
+                est = out
+            else:
+                est = torch.zeros(2 * mix_flat.numel(), dtype=torch.float32, device=self.device) \
+                    if _needs_zero_fill(offs, lens, mix_flat.numel()) else \
+                    torch.empty(2 * mix_flat.numel(), dtype=torch.float32, device=self.device)
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             if debug is None:
                 rc = self.lib.resep_forward(self.handle, mix_flat.data_ptr(), c_off, c_len, B, est.data_ptr(),
@@ -134,7 +153,28 @@ def _resep_separate(mix_flat: torch.Tensor, offs: list[int], lens: list[int], en
     eng = _ENGINES.get(engine)
     if eng is None:
         raise RuntimeError("clearconverse_b200: separator engine was destroyed")
-    return eng.forward(mix_flat, offs, lens, precision, batch_mode)
+    mix_buf, est_buf = eng.static_io(offs, lens, mix_flat.numel())
+    mix_buf.copy_(mix_flat)
+    eng.forward(mix_buf, offs, lens, precision, batch_mode, out=est_buf)
+    return est_buf.clone()                      # a new tensor owned by the caller, as upstream returns
+
+
+@torch.library.custom_op("clearconverse_b200::resep_separate_static", mutates_args=(), device_types="cuda")
+def _resep_separate_static(host_or_dev_mix: torch.Tensor, offs: list[int], lens: list[int], engine: int, precision: int,
+                           batch_mode: int, slot: int) -> torch.Tensor:
+    """Like resep_separate, but returns the engine's persistent output buffer of `slot` itself (no clone): the
+    pipelined driver copies it to the host and only reuses the slot after that copy has completed."""
+    eng = _ENGINES.get(engine)
+    if eng is None:
+        raise RuntimeError("clearconverse_b200: separator engine was destroyed")
+    _, est_buf = eng.static_io(offs, lens, host_or_dev_mix.numel(), slot)
+    eng.forward(host_or_dev_mix, offs, lens, precision, batch_mode, out=est_buf)
+    return est_buf
+
+
+@_resep_separate_static.register_fake
+def _(host_or_dev_mix, offs, lens, engine, precision, batch_mode, slot):
+    return host_or_dev_mix.new_empty(2 * host_or_dev_mix.numel())
 
 
 @_resep_separate.register_fake
@@ -320,14 +360,16 @@ class SepformerSeparation:
         for i, mix in enumerate(batches):
             self._check_mix(mix)
             B, T = mix.shape
+            offs, lens, slot = [b * T for b in range(B)], [T] * B, i % depth
+            # slot i % depth was last used by batch i - depth, whose result has been drained (synchronised) already
+            mix_buf, _ = self._engine.static_io(offs, lens, B * T, slot)
             with torch.cuda.stream(h2d):
-                dmix = mix.to(dev, non_blocking=True)
+                mix_buf.copy_(mix.reshape(-1), non_blocking=True)
                 up = torch.cuda.Event(); up.record(h2d)
             compute.wait_event(up)
-            dmix.record_stream(compute)
-            est = torch.ops.clearconverse_b200.resep_separate(
-                dmix.view(-1), [b * T for b in range(B)], [T] * B, self._engine.id,
-                _lib.PRECISIONS[self.precision], _lib.BATCH_MODES[self.batch_mode]).view(B, T, NUM_SPKS)
+            est = torch.ops.clearconverse_b200.resep_separate_static(
+                mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision],
+                _lib.BATCH_MODES[self.batch_mode], slot).view(B, T, NUM_SPKS)
             done = torch.cuda.Event(); done.record(compute)
             if out_buffers is not None:
                 host = out_buffers[i % len(out_buffers)]
@@ -336,7 +378,6 @@ class SepformerSeparation:
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
                 host.copy_(est, non_blocking=True)
-                est.record_stream(d2h)
                 down = torch.cuda.Event(); down.record(d2h)
             inflight.append((down, host))
             if len(inflight) >= depth:
