@@ -76,6 +76,8 @@ def kernel_work(name: str, batch: int, t: int):
         return "tensor", rows * (32_768 + 524_288)
     if name.startswith("k_qkv_tc"):                    # fused LN1 + in-projection
         return "tensor", rows * 98_304
+    if name.startswith("k_attention_bf16_tma"):        # every intra chunk (TMA-fed per-(chunk, head) kernel)
+        return "tensor", att_intra
     if name.startswith("k_attention_bf16_short"):      # sequences <= 160 rows (every intra chunk)
         return "tensor", att_intra + sum(8 * 4 * n * n * 128 for n in mem_seqs if n <= 160)
     if name.startswith("k_attention"):

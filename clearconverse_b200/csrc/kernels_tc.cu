@@ -611,16 +611,172 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
   }
 }
 
+// Per-(chunk, head) attention for equal-length sequences of <= 160 rows with the Q / K / V slices fetched by TMA.
+// In k_attention_bf16_short every warp-level load touches 32 different rows (768-byte stride), i.e. 32 L1 tag lookups
+// per instruction: an ablation (9 of 10 key blocks removed) still took 31 of the kernel's 41 us -- the per-CTA
+// prologue, serialised in the LSU, was the bottleneck, not the exp2 / HMMA work.  Three TMA boxes ([160 rows x 32 B],
+// 32B-swizzled so that ldmatrix reads them conflict-free) do the same strided gather without the LSU.
+// Rows past the sequence inside a box belong to the next chunk: as keys they are masked (last block), as queries
+// they are computed and never stored; past the end of the tensor TMA fills zeros.
+__global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx,
+                                                                int seq_len) {
+  __shared__ __align__(256) bf16 Qs[160 * 16];
+  __shared__ __align__(256) bf16 Ks[160 * 16];
+  __shared__ __align__(256) bf16 Vs[160 * 16];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_kmax[5];
+  pdl_trigger();
+  const int len = seq_len;
+  const int head = blockIdx.y;
+  const int64_t off = (int64_t)blockIdx.x * seq_len;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    pdl_wait();                                      // qkv comes from the previous kernel in the stream
+    mbar_arrive_expect_tx(&bar, 3 * 160 * 32);
+    tma_load_2d(Qs, &tmQKV, &bar, head * DH, (int)off);
+    tma_load_2d(Ks, &tmQKV, &bar, D + head * DH, (int)off);
+    tma_load_2d(Vs, &tmQKV, &bar, 2 * D + head * DH, (int)off);
+  }
+  __syncthreads();                                   // barrier initialised
+  mbar_wait(&bar, 0);
+  {  // largest squared key norm (one key row per thread; rows past the sequence only loosen the bound)
+    const uint4* kr = reinterpret_cast<const uint4*>(Ks + threadIdx.x * 16);
+    const uint4 ka = kr[0], kb = kr[1];
+    const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+    float kn2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
+      kn2 = fmaf(f.x, f.x, kn2);
+      kn2 = fmaf(f.y, f.y, kn2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
+    if (lane == 0) s_kmax[warp] = kn2;
+  }
+  __syncthreads();
+  const float kmax2 = fmaxf(fmaxf(fmaxf(s_kmax[0], s_kmax[1]), fmaxf(s_kmax[2], s_kmax[3])), s_kmax[4]);
+  const int nkk = (len + 15) >> 4;
+  constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
+  constexpr uint32_t ONES = 0x3F803F80u;
+  // ldmatrix lane addressing in a [rows x 32 B] tile with the 32B swizzle (16-byte chunk ^= (row >> 2) & 1):
+  // matrix m = lane / 8, row lane % 8; every row base below is a multiple of 8, so the swizzle bit is (lane % 8) >> 2
+  const int lm = lane >> 3, lr = lane & 7, sw = lr >> 2;
+  const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * 16 + (((lm & 1) ^ sw) << 3);   // m0/m1 = dh halves of keys 0-7, m2/m3 of keys 8-15
+  const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * 16 + (((lm >> 1) ^ sw) << 3);   // m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
+  const bf16* q_lane = Qs + ((lm & 1) * 8 + lr) * 16 + (((lm >> 1) ^ sw) << 3);   // a0..a3 of the m16k16 A fragment
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    const int row0 = warp * 32 + mt * 16;
+    if (row0 >= len) break;                            // warp-uniform
+    uint32_t qa[4];
+    ldmatrix_x4(qa, q_lane + row0 * 16);
+    // softmax stabiliser from the Cauchy-Schwarz bound (see k_attention_bf16_short); exact row maxima as fallback
+    float qn0, qn1;
+    {
+      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[0]));
+      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[1]));
+      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[2]));
+      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[3]));
+      qn0 = a0.x * a0.x + a0.y * a0.y + a2.x * a2.x + a2.y * a2.y;
+      qn1 = a1.x * a1.x + a1.y * a1.y + a3.x * a3.x + a3.y * a3.y;
+      qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
+      qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
+    }
+    float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;
+    float mb = fmaxf(mx0, mx1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    if (!(mb * 0.5f < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs
+      mx0 = -INFINITY; mx1 = -INFINITY;
+#pragma unroll 1
+      for (int kk = 0; kk < nkk; ++kk) {
+        uint32_t kf[4];
+        ldmatrix_x4(kf, k_lane + kk * 16 * 16);
+        float s0[4], s1[4];
+        mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
+        mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+        if (c + 1 >= len) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+        if (c + 8 >= len) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
+        if (c + 9 >= len) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
+        mx1 = fmaxf(mx1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    }
+    const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, ol[4] = {0.f, 0.f, 0.f, 0.f};
+    auto pv_block = [&](int kk, auto mask_c) {
+      constexpr bool MASK = decltype(mask_c)::value;
+      uint32_t kf[4], vf[4];
+      ldmatrix_x4(kf, k_lane + kk * 16 * 16);
+      ldmatrix_x4_trans(vf, v_lane + kk * 16 * 16);
+      float s0[4], s1[4];
+      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
+      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
+      s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
+      s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
+      s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
+      s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
+      if (MASK) {
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
+        if (c + 1 >= len) { s0[1] = 0.f; s0[3] = 0.f; }
+        if (c + 8 >= len) { s1[0] = 0.f; s1[2] = 0.f; }
+        if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
+      }
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s0[0], s0[1]);
+      pa[1] = pack_bf16(s0[2], s0[3]);
+      pa[2] = pack_bf16(s1[0], s1[1]);
+      pa[3] = pack_bf16(s1[2], s1[3]);
+      mma_bf16_16816(o0, pa, vf[0], vf[1]);
+      mma_bf16_16816(o1, pa, vf[2], vf[3]);
+      mma_bf16_16816(ol, pa, ONES, ONES);              // row sums of the bf16-rounded P (every column is the row sum)
+    };
+#pragma unroll 3
+    for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
+    pv_block(nkk - 1, std::true_type{});
+    const float i0 = 1.f / ol[0], i1 = 1.f / ol[2];
+    const int r0 = row0 + g, r1 = row0 + g + 8;
+    if (r0 < len) {
+      bf16* op = ctx + (off + r0) * D + head * DH + 2 * t4;
+      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[0] * i0, o0[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[0] * i0, o1[1] * i0);
+    }
+    if (r1 < len) {
+      bf16* op = ctx + (off + r1) * D + head * DH + 2 * t4;
+      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[2] * i1, o0[3] * i1);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[2] * i1, o1[3] * i1);
+    }
+  }
+}
+
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
                                  const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st) {
   const int longest = tile_seq == nullptr ? seq_len : max_len;
-  ProfScope prof_scope(h, longest <= 160 ? "k_attention_bf16_short" : longest <= 448 ? "k_attention_bf16_mid" : "k_attention_bf16", st);
+  ProfScope prof_scope(h, longest <= 160 ? (tile_seq == nullptr ? "k_attention_bf16_tma" : "k_attention_bf16_short") : longest <= 448 ? "k_attention_bf16_mid" : "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
   // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
   // of the next tile with identical results).
   if (tile_seq == nullptr) {
     if (n_seq == 0) return RESEP_OK;
-    if (seq_len <= 160) {
+    static const bool use_tma = !(getenv("RESEP_ATTN_TMA") && getenv("RESEP_ATTN_TMA")[0] == '0');
+    if (seq_len <= 160 && use_tma && (int64_t)n_seq * seq_len < 2000000000LL) {
+      CUtensorMap tmQKV;
+      int rc = make_tmap_head(h, &tmQKV, qkv, (int64_t)n_seq * seq_len, 3 * D, 160);
+      if (rc) return rc;
+      RESEP_CUDA(h, launch_pdl(k_attention_bf16_tma, dim3((unsigned)n_seq, NH), dim3(160), 0, st, tmQKV, ctx, seq_len));
+    } else if (seq_len <= 160) {
       RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<160, 5, 2>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len,
                                (const int*)nullptr, 1));
     } else if (seq_len <= 448) {
