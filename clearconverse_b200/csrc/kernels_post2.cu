@@ -136,6 +136,9 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();                           // the next kernel's prologue may overlap this kernel's tail
   int tr_n = 0;
+#ifdef RESEP_TRACE_BUILD
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.trace[1535] = clock64();
+#endif
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -161,6 +164,9 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   cluster_sync_all();                      // barriers of both CTAs are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef RESEP_TRACE_BUILD
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.trace[1534] = clock64();
+#endif
 
   // Programmatic dependent launch: the weight ring is filled without waiting for the previous kernel (attention,
   // which produces ctx); every other role touches ctx / o and waits for it to complete first.
@@ -345,35 +351,61 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
     auto E1 = [&](int t) {
       const uint32_t ycol = lane_base + 128u * (uint32_t)(t % 3) + 64 * hf;
       if (tracer) TR(1, 1000 + t);
-      mbar_wait(out_full, t & 1);
+      // While the out-proj of this tile is still on the tensor pipe (group A would only wait): r = o + bo for this
+      // thread's 64 columns.  The first 32 stay in registers; the other 32 are parked in Y2[t & 1] (free until this
+      // very E1 writes the LayerNorm output there), so nothing spills and the critical path after `out_full` has no
+      // shared-memory loads before the statistics.
       mbar_wait(res_full, t & 1);
-      tc_fence_after();
-      if (tracer) TR(1, 1100 + t);
       float2 v[32];
-      tmem_ld32(ycol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(ycol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[16]));
-      tmem_ld_wait();
-      if (tracer) TR(1, 1110 + t);
-      // o' = acc + bo + o; row statistics from the plain sums of this thread's 64 columns (one exchange per row)
-      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+      const uint32_t park = lane_base + TM_Y2 + 64 * (t & 1) + 32 * hf;
+      {
+        float2 rp[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 b = *reinterpret_cast<const float4*>(s_bo + 64 * hf + 4 * j);
-        const float4 o4 = *reinterpret_cast<const float4*>(smem + OFF_RES + sw128_f32_off(r, 64 * hf + 4 * j));
-        const float2 x0 = fadd2(v[2 * j], fadd2(make_float2(b.x, b.y), make_float2(o4.x, o4.y)));
-        const float2 x1 = fadd2(v[2 * j + 1], fadd2(make_float2(b.z, b.w), make_float2(o4.z, o4.w)));
-        s1 = fadd2(s1, fadd2(x0, x1));
-        s2 = ffma2(x0, x0, s2);
-        s2 = ffma2(x1, x1, s2);
-        v[2 * j] = x0;
-        v[2 * j + 1] = x1;
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = *reinterpret_cast<const float4*>(s_bo + 64 * hf + 4 * j);
+          const float4 o4 = *reinterpret_cast<const float4*>(smem + OFF_RES + sw128_f32_off(r, 64 * hf + 4 * j));
+          const float2 r0 = fadd2(make_float2(b.x, b.y), make_float2(o4.x, o4.y));
+          const float2 r1 = fadd2(make_float2(b.z, b.w), make_float2(o4.z, o4.w));
+          if (j < 8) { v[2 * j] = r0; v[2 * j + 1] = r1; }
+          else { rp[2 * (j - 8)] = r0; rp[2 * (j - 8) + 1] = r1; }
+        }
+        tmem_st32(park, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
+        tmem_st_wait();
       }
-      tmem_st32(ycol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));        // o' stays in TMEM: FFN2 accumulates onto it
-      tmem_st32(ycol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[16]));
-      s_sum[hf * 128 + r] = s1.x + s1.y;
-      s_sq[hf * 128 + r] = s2.x + s2.y;
       __syncwarp();
       if (lane == 0) mbar_arrive(res_empty);     // the residual tile may be refilled
+      mbar_wait(out_full, t & 1);
+      tc_fence_after();
+      if (tracer) TR(1, 1100 + t);
+      // o' = acc + r; row statistics from the plain sums of this thread's 64 columns (one exchange per row)
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+      {
+        float2 acc[16];
+        tmem_ld32(ycol, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+        tmem_ld32(park, *reinterpret_cast<uint32_t(*)[32]>(&v[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 x = fadd2(acc[j], v[j]);
+          s1 = fadd2(s1, x);
+          s2 = ffma2(x, x, s2);
+          v[j] = x;
+        }
+        tmem_st32(ycol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));        // o' stays in TMEM: FFN2 accumulates onto it
+        tmem_ld32(ycol + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 x = fadd2(acc[j], v[16 + j]);
+          s1 = fadd2(s1, x);
+          s2 = ffma2(x, x, s2);
+          v[16 + j] = x;
+        }
+        tmem_st32(ycol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[16]));
+      }
+      if (tracer) TR(1, 1110 + t);
+      s_sum[hf * 128 + r] = s1.x + s1.y;
+      s_sq[hf * 128 + r] = s2.x + s2.y;
       if (tracer) TR(1, 1120 + t);
       abar();
       if (tracer) TR(1, 1130 + t);
@@ -504,7 +536,13 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
     if (elected) tma_store_wait<0>();
   }
   tc_fence_before();
+#ifdef RESEP_TRACE_BUILD
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.trace[1533] = clock64();
+#endif
   cluster_sync_all();                      // the leader's MMAs read the peer's shared memory: nobody leaves early
+#ifdef RESEP_TRACE_BUILD
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.trace[1532] = clock64();
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair<512>(tmem);
