@@ -183,7 +183,7 @@ def run_reference(args, rank):
         return
     from clearconverse_b200 import weights
     sds = weights.random_init_state_dicts(0)
-    items = 2
+    items = BATCH          # the whole configs[1] batch per step (coupled semantics depend on the batch composition)
     import torch
     from clearconverse_b200 import synth
     cores = os.cpu_count() or 1
