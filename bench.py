@@ -64,6 +64,10 @@ def kernel_work(name: str, batch: int, t: int):
     attention 76,800, out-proj 32,768, FFN 524,288."""
     L, S, chunks, M, mem_seqs = shapes(batch, t)
     rows = 16 * M + 8 * chunks                         # token-layers: 16 intra layers + 8 memory layers
+    if name.endswith("(small)"):                       # the memory transformer's launches of the CTA-pair kernels
+        rows, name = 8 * chunks, name[:-7]
+    elif name.startswith("k_post2_tc") or name.startswith("k_qkv2_tc"):
+        rows = 16 * M
     att_intra = 16 * chunks * 8 * 4 * 150 * 150 * 16
     att = att_intra + 8 * sum(4 * n * n * 128 for n in mem_seqs)
     if name.startswith("k_gemm_tc<bf16,bf16"):        # QKV + FFN1
@@ -74,8 +78,8 @@ def kernel_work(name: str, batch: int, t: int):
         return "tensor", M * 65_536
     if name.startswith("k_post"):                      # fused out-proj + LN2 + FFN1 + ReLU + FFN2 (+ residuals); k_post2_tc = CTA-pair version
         return "tensor", rows * (32_768 + 524_288)
-    if name.startswith("k_qkv_tc"):                    # fused LN1 + in-projection
-        return "tensor", rows * 98_304
+    if name.startswith("k_qkv"):                       # fused LN1 + in-projection: 512 B in + 768 B out per row, HBM-bound
+        return "hbm", rows * (512 + 768)
     if name.startswith("k_attention_bf16_tma"):        # every intra chunk (TMA-fed per-(chunk, head) kernel)
         return "tensor", att_intra
     if name.startswith("k_attention_bf16_short"):      # sequences <= 160 rows (every intra chunk)
@@ -334,9 +338,7 @@ def main():
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f).get(name.split("<")[0])
             if tj:
-                L, S, chunks, M, _ = shapes(BATCH, T)
-                big, small = 16, rec["launches"] / reps - 16          # intra-block launches (M rows) and memory-block launches (chunks rows)
-                traffic = tj["dram_bytes_big_launch"] * (big + small * chunks / M) / (big + small)
+                traffic = tj["dram_bytes_big_launch"]            # the 16 intra-block launches (64,800 rows each)
         except Exception:
             traffic = None
         roofline = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,

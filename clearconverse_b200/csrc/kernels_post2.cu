@@ -551,7 +551,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
 
 int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st) {
   if (rows <= 0) return RESEP_OK;
-  ProfScope prof_scope(h, "k_post2_tc", st);
+  // the memory transformer runs the same kernel on a few hundred rows (latency-bound): timed under its own name
+  ProfScope prof_scope(h, rows >= 8192 ? "k_post2_tc" : "k_post2_tc(small)", st);
   const bool split = h->w16_mode >= 1, split_ffn = h->w16_mode == 1;
   CUtensorMap tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L;
   int rc;

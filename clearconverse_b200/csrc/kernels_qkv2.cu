@@ -286,7 +286,8 @@ k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUten
 
 int launch_qkv2_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv, int64_t rows, cudaStream_t st) {
   if (rows <= 0) return RESEP_OK;
-  ProfScope prof_scope(h, "k_qkv2_tc", st);
+  // the memory transformer runs the same kernel on a few hundred rows (latency-bound): timed under its own name
+  ProfScope prof_scope(h, rows >= 8192 ? "k_qkv2_tc" : "k_qkv2_tc(small)", st);
   const bool split = h->w16_mode >= 1;
   CUtensorMap tmO, tmW, tmWL, tmQ;
   int rc;
