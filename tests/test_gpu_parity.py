@@ -295,3 +295,19 @@ def test_bf16_graph_replay_is_bit_identical_to_eager(make_sep):
         assert torch.equal(o, outs[0])
     other = sep.separate_batch(synth_batch(2, 8000, 62))          # same shapes, other data, replayed graph
     assert not torch.equal(other, outs[0]) and torch.isfinite(other).all()
+
+
+def test_bf16_ragged_independent_segments(make_sep, oracle):
+    """The config-4 path: a length-ragged batch in the bf16 mode with per-item memory sequences (ragged
+    attention kernel for the memory transformer), each segment against its own B=1 oracle call."""
+    sep = make_sep("bf16", "independent")
+    lens = [4000, 16, 9000, 1211, 32000, 2500]
+    segs = [synth_mixture(n, 70 + i)[0] for i, n in enumerate(lens)]
+    outs = sep.separate_segments(segs)
+    for s, o in zip(segs, outs):
+        want = oracle.separate_batch(s[None])[0]
+        got = o.cpu()
+        assert got.shape == want.shape and torch.isfinite(got).all()
+        assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
+        if s.numel() >= 1000:
+            assert si_snr_db(got.T[None], want.T[None]).min().item() > 35.0
