@@ -643,7 +643,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
   }
   __syncthreads();                                   // barrier initialised
   mbar_wait(&bar, 0);
-  {  // largest squared key norm (one key row per thread; rows past the sequence only loosen the bound)
+  {  // largest squared key norm, one key row per thread.  Rows past the sequence (the next chunk's rows inside the
+     // box) are excluded: the result of a chunk must not depend on what follows it in the buffer.
     const uint4* kr = reinterpret_cast<const uint4*>(Ks + threadIdx.x * 16);
     const uint4 ka = kr[0], kb = kr[1];
     const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
@@ -654,6 +655,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
       kn2 = fmaf(f.x, f.x, kn2);
       kn2 = fmaf(f.y, f.y, kn2);
     }
+    if ((int)threadIdx.x >= len) kn2 = 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
     if (lane == 0) s_kmax[warp] = kn2;
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
     float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;
-    float mb = fmaxf(mx0, mx1);
+    float mb = fmaxf(row0 + g < len ? mx0 : 0.f, row0 + g + 8 < len ? mx1 : 0.f);   // query rows past the sequence do not vote
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
     if (!(mb * 0.5f < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs

@@ -447,8 +447,25 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     mem.seq_len = (int)p->n_chunks; mem.seq_off = nullptr; mem.pos = nullptr; mem.tile_seq = nullptr; mem.tile_q0 = nullptr;
   }
 
+  // The intra blocks are row-local per chunk, so large batches run them in SLICES of whole chunks: 378 chunks =
+  // 56,700 rows = 221.5 pair-tiles fill the 74 CTA pairs for exactly three rounds (no wave-quantisation loss) and
+  // keep a slice's residual stream + qkv + ctx (87 MB) inside the 126 MB L2; the per-slice scratch (o, qkv, ctx)
+  // reuses the same addresses for every slice.  Batches of up to 512 chunks run as one slice.
+  static const int64_t slice_env = getenv("RESEP_SLICE_CHUNKS") ? atoll(getenv("RESEP_SLICE_CHUNKS")) : 378;
+  const int64_t slice = (p->n_chunks <= 512 || slice_env <= 0) ? p->n_chunks : slice_env;
+  auto run_intra = [&](int blk, const float* xprev, const float* hc, float* xin, float* out, float* seq_mean,
+                       bf16* prelu_out_) -> int {
+    for (int64_t c0 = 0; c0 < p->n_chunks; c0 += slice) {
+      const int64_t nc = std::min<int64_t>(slice, p->n_chunks - c0), r0 = c0 * CHUNK * D;
+      SeqDesc sl{nc * CHUNK, (int)nc, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK};
+      int rc2 = run_block(h, blk, xprev + r0, hc ? hc + c0 * D : nullptr, xin + r0, ws.o, out + r0,
+                          seq_mean ? seq_mean + c0 * D : nullptr, sl, ws, precision, st, prelu_out_ ? prelu_out_ + r0 : nullptr);
+      if (rc2) return rc2;
+    }
+    return RESEP_OK;
+  };
   // seg_model[0](x + 0): skip input is the encoder output itself
-  if ((rc = run_block(h, 0, ws.x0, nullptr, ws.x0, ws.o, ws.a, ws.hc_in, intra, ws, precision, st))) return rc;
+  if ((rc = run_intra(0, ws.x0, nullptr, ws.x0, ws.a, ws.hc_in, nullptr))) return rc;
   if (dbg && dbg->seg0) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg0, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (dbg && dbg->chunk_mean)
     RESEP_CUDA(h, cudaMemcpyAsync(dbg->chunk_mean, ws.hc_in, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -458,8 +475,9 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     RESEP_CUDA(h, cudaMemcpyAsync(dbg->mem0, ws.hc_out, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // seg_model[1](out + hc)
   // in the bf16 mode the block epilogue also emits PReLU(out) in bf16 (ws.y), the A operand of output_fc
-  bf16* prelu_out = precision == RESEP_PREC_BF16 ? reinterpret_cast<bf16*>(ws.y) : nullptr;
-  if ((rc = run_block(h, 1, ws.a, ws.hc_out, ws.a, ws.o, ws.a, nullptr, intra, ws, precision, st, prelu_out))) return rc;
+  // (the upper half of ws.y: its lower half stays per-slice scratch of the unfused layer path)
+  bf16* prelu_out = precision == RESEP_PREC_BF16 ? reinterpret_cast<bf16*>(ws.y) + align_up((size_t)p->M, 128) * D : nullptr;
+  if ((rc = run_intra(1, ws.a, ws.hc_out, ws.a, ws.a, nullptr, prelu_out))) return rc;
   if (dbg && dbg->seg1) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg1, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // output_fc (PReLU -> 1x1 conv 128->256) -> ReLU mask -> x encoder features -> decoder
@@ -468,7 +486,8 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     if ((rc = launch_prelu(h, ws.a, h->w.prelu_a, ws.y, p->M * D, st))) return rc;
     if ((rc = launch_gemm_f32(h, ws.y, h->w.fc_w, h->w.fc_b, nullptr, mask, p->M, NSPK * D, D, true, st))) return rc;
   } else {
-    if ((rc = tc_run_mask(h, ws.a, ws.y, mask, p->M, precision, st, prelu_out != nullptr))) return rc;
+    float* y_mask = prelu_out ? reinterpret_cast<float*>(prelu_out) : ws.y;
+    if ((rc = tc_run_mask(h, ws.a, y_mask, mask, p->M, precision, st, prelu_out != nullptr))) return rc;
   }
   return launch_decoder(h, mask, ws.x0, *p, est, st);
 }

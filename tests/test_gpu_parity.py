@@ -265,9 +265,11 @@ def test_config3_long_sequence_properties(make_sep, oracle):
     assert (tf - want).abs().max().item() <= TOL_SPEC
 
 
-def test_independent_mode_is_batch_composition_invariant(make_sep):
-    """Sharding property: an item's result does not depend on what else is in the batch."""
-    sep = make_sep("fp32", "independent")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_independent_mode_is_batch_composition_invariant(make_sep, precision):
+    """Sharding property: an item's result does not depend on what else is in the batch (bit for bit, also in the
+    bf16 mode: the attention stabiliser ignores the neighbouring chunk's rows inside its TMA box)."""
+    sep = make_sep(precision, "independent")
     segs = [synth_mixture(n, 90 + i)[0] for i, n in enumerate([4000, 9000, 1600, 32000])]
     all_at_once = sep.separate_segments(segs)
     rev = sep.separate_segments(segs[::-1])[::-1]
@@ -311,3 +313,25 @@ def test_bf16_ragged_independent_segments(make_sep, oracle):
         assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
         if s.numel() >= 1000:
             assert si_snr_db(got.T[None], want.T[None]).min().item() > 35.0
+
+
+def test_sliced_intra_blocks_match_unsliced(sds, cuda_lib_built):
+    """Batches of more than 512 chunks run the intra blocks in slices (L2-sized, wave-aligned); the result must not
+    depend on the slicing.  20 x 4 s = 540 chunks, compared with RESEP_SLICE_CHUNKS=0 (one slice) in a subprocess."""
+    import subprocess, sys, tempfile
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from clearconverse_b200 import SepformerSeparation, synth, weights\n"
+        "sep = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision=sys.argv[2], batch_mode='coupled')\n"
+        "out = sep.separate_batch(synth.synth_batch(20, 32000, 9)).cpu()\n"
+        "torch.save(out, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = {}
+    with tempfile.TemporaryDirectory() as d:
+        for prec in ("fp32", "bf16"):
+            for sl in ("378", "0", "100"):
+                path = os.path.join(d, f"{prec}_{sl}.pt")
+                env = dict(os.environ, RESEP_SLICE_CHUNKS=sl)
+                subprocess.run([sys.executable, "-c", code, path, prec], check=True, env=env)
+                outs[(prec, sl)] = torch.load(path)
+    for prec in ("fp32", "bf16"):
+        assert torch.equal(outs[(prec, "378")], outs[(prec, "0")]) and torch.equal(outs[(prec, "100")], outs[(prec, "0")])
