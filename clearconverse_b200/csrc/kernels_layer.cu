@@ -629,7 +629,7 @@ int launch_qkv_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv,
   if ((rc = make_tmap<bf16>(h, &tmW, lw.in_w_bf, 3 * D, D, 128))) return rc;
   if ((rc = make_tmap<bf16>(h, &tmWL, lw.in_w_bl, 3 * D, D, 128))) return rc;
   if ((rc = make_tmap<bf16>(h, &tmQ, qkv, rows, 3 * D, 128))) return rc;
-  QkvArgs a{lw.norm1_w, lw.norm1_b, lw.in_b, rows};
+  QkvArgs a{lw.norm1_w, lw.norm1_b, lw.in_b_hi, rows};
   const int tiles = (int)((rows + 127) / 128);
   const int grid = tiles < h->sm_count ? tiles : h->sm_count;
   if (split) {

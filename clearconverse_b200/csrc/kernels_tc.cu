@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
+  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * QKV_HEAD_STRIDE;
 
   // Q fragments of this warp's two m16 tiles (rows beyond the sequence read as zero)
   uint32_t qa[2][4];
@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[mt][hh][i] = 0.f;   // o[mt][ntile][c]
     }
-  constexpr float SCALE_LOG2E = 0.25f * 1.4426950408889634f;
 
   for (int kt = 0; kt < len; kt += AKT) {
     __syncthreads();
@@ -320,9 +319,9 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
       const int key = kt + threadIdx.x;
       uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
       if (key < len) {
-        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
+        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + QKV_K);
         k0 = p[0]; k1 = p[1];
-        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
+        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + QKV_V);
         v0 = pv[0]; v1 = pv[1];
       }
       uint32_t* kd = reinterpret_cast<uint32_t*>(Ks + threadIdx.x * KS_STRIDE);
@@ -351,10 +350,10 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 #pragma unroll
       for (int j = 0; j < AKT / 8; ++j) {
         const int c = 8 * j + 2 * t4;
-        s[j][0] = (c < nvalid) ? s[j][0] * SCALE_LOG2E : -INFINITY;
-        s[j][1] = (c + 1 < nvalid) ? s[j][1] * SCALE_LOG2E : -INFINITY;
-        s[j][2] = (c < nvalid) ? s[j][2] * SCALE_LOG2E : -INFINITY;
-        s[j][3] = (c + 1 < nvalid) ? s[j][3] * SCALE_LOG2E : -INFINITY;
+        s[j][0] = (c < nvalid) ? s[j][0] : -INFINITY;
+        s[j][1] = (c + 1 < nvalid) ? s[j][1] : -INFINITY;
+        s[j][2] = (c < nvalid) ? s[j][2] : -INFINITY;
+        s[j][3] = (c + 1 < nvalid) ? s[j][3] : -INFINITY;
         mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
         mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
       }
@@ -448,7 +447,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
   const int head = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * DH;
+  const bf16* qbase = qkv + (int64_t)off * (3 * D) + head * QKV_HEAD_STRIDE;
   __shared__ float s_kmax[WARPS];
   // Q fragments of this warp's two m16 tiles, requested before the K / V rows so that the CTA pays one global-memory
   // latency, not three (rows past the sequence read as zero)
@@ -473,9 +472,9 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
     for (int key = threadIdx.x; key < kp; key += THREADS) {
       uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
       if (key < len) {
-        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + D);
+        const uint4* p = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + QKV_K);
         k0 = p[0]; k1 = p[1];
-        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + 2 * D);
+        const uint4* pv = reinterpret_cast<const uint4*>(qbase + (int64_t)key * (3 * D) + QKV_V);
         v0 = pv[0]; v1 = pv[1];
       }
       uint4* kd = reinterpret_cast<uint4*>(Ks + key * AS_ROW);
@@ -501,7 +500,6 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
 #pragma unroll
   for (int i = 1; i < WARPS; ++i) kmax2 = fmaxf(kmax2, s_kmax[i]);
   const int nkk = (len + 15) >> 4;                    // 16-key blocks holding at least one valid key
-  constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
   // ldmatrix lane addressing: matrix m = lane / 8, row lane % 8
   const int lm = lane >> 3, lr = lane & 7;
   const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * AS_ROW + (lm & 1) * 8;   // K: m0/m1 = dh halves of tile A, m2/m3 of tile B
@@ -550,7 +548,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       mx0 = fmaxf(mx0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
       mx1 = fmaxf(mx1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
     };
-    if (!(mb * 0.5f < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs
+    if (!(mb * (0.5f / QK_PRESCALE) < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs
       // ---- exact pass: row maxima of the raw scores
       mx0 = -INFINITY; mx1 = -INFINITY;
 #pragma unroll 1
@@ -561,8 +559,8 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     }
-    const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
-    // ---- pass 2: p = exp2(s * SC - max * SC); O += P . V; row sums of the bf16-rounded P from a third MMA against an
+    const float nb0 = -mx0, nb1 = -mx1;               // k is pre-scaled (QK_PRESCALE): scores are base-2 exponents
+    // ---- pass 2: p = exp2(s - max) (k pre-scaled); O += P . V; row sums of the bf16-rounded P from a third MMA against an
     // all-ones B fragment (every column of that accumulator is the row sum, so no add chain and no shuffle)
     float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, ol[4] = {0.f, 0.f, 0.f, 0.f};
     auto pv_block = [&](int kk, auto mask_c) {
@@ -571,12 +569,10 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
       ldmatrix_x4_trans(vf, v_lane + kk * 16 * AS_ROW);
       float s0[4], s1[4];
-      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
-      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
-      s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
-      s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
-      s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
-      s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
+      mma_bf16_16816_c(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
+      mma_bf16_16816_c(s1, qa, kf[2], kf[3], nb0, nb1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s0[i] = ex2_approx(s0[i]); s1[i] = ex2_approx(s1[i]); }
       if (MASK) {
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
@@ -611,18 +607,21 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
   }
 }
 
-// Per-(chunk, head) attention for equal-length sequences of <= 160 rows with the Q / K / V slices fetched by TMA.
+// Per-(chunk, head) attention for equal-length sequences of <= 160 rows with the head's q | k | v slice fetched by TMA.
 // In k_attention_bf16_short every warp-level load touches 32 different rows (768-byte stride), i.e. 32 L1 tag lookups
 // per instruction: an ablation (9 of 10 key blocks removed) still took 31 of the kernel's 41 us -- the per-CTA
-// prologue, serialised in the LSU, was the bottleneck, not the exp2 / HMMA work.  Three TMA boxes ([160 rows x 32 B],
-// 32B-swizzled so that ldmatrix reads them conflict-free) do the same strided gather without the LSU.
+// prologue, serialised in the LSU, was the bottleneck, not the exp2 / HMMA work.  TMA does the strided gather without
+// the LSU, but the SM's TMA unit serves about one box ROW per 2.7 cycles whatever its width (three [160 x 32 B]
+// boxes per CTA, 23 CTAs per SM = 30k cycles = the 17 us "empty kernel" time of the first TMA version).  The bf16
+// qkv buffer is therefore head-interleaved (QKV_HEAD_STRIDE): ONE [160 rows x 128 B] box holds q | k | v of the head
+// (+ 32 B of the next head, unused; zero-filled past column 384), 128B-swizzled so ldmatrix reads it conflict-free.
 // Rows past the sequence inside a box belong to the next chunk: as keys they are masked (last block), as queries
 // they are computed and never stored; past the end of the tensor TMA fills zeros.
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx,
                                                                 int seq_len) {
-  __shared__ __align__(256) bf16 Qs[160 * 16];
-  __shared__ __align__(256) bf16 Ks[160 * 16];
-  __shared__ __align__(256) bf16 Vs[160 * 16];
+  __shared__ __align__(1024) bf16 Ts[160 * 64];      // row r: 16-byte chunk c at c ^ (r & 7); chunks 0,1 = q, 2,3 = k, 4,5 = v
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_kmax[5];
   pdl_trigger();
@@ -636,17 +635,16 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     mbar_init(&bar, 1);
     fence_barrier_init();
     pdl_wait();                                      // qkv comes from the previous kernel in the stream
-    mbar_arrive_expect_tx(&bar, 3 * 160 * 32);
-    tma_load_2d(Qs, &tmQKV, &bar, head * DH, (int)off);
-    tma_load_2d(Ks, &tmQKV, &bar, D + head * DH, (int)off);
-    tma_load_2d(Vs, &tmQKV, &bar, 2 * D + head * DH, (int)off);
+    mbar_arrive_expect_tx(&bar, 160 * 128);
+    tma_load_2d(Ts, &tmQKV, &bar, head * QKV_HEAD_STRIDE, (int)off);
   }
   __syncthreads();                                   // barrier initialised
   mbar_wait(&bar, 0);
   {  // largest squared key norm, one key row per thread.  Rows past the sequence (the next chunk's rows inside the
      // box) are excluded: the result of a chunk must not depend on what follows it in the buffer.
-    const uint4* kr = reinterpret_cast<const uint4*>(Ks + threadIdx.x * 16);
-    const uint4 ka = kr[0], kb = kr[1];
+    const int r7 = threadIdx.x & 7;
+    const uint4 ka = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((2 ^ r7) << 3));
+    const uint4 kb = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((3 ^ r7) << 3));
     const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
     float kn2 = 0.f;
 #pragma unroll
@@ -663,20 +661,19 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
   __syncthreads();
   const float kmax2 = fmaxf(fmaxf(fmaxf(s_kmax[0], s_kmax[1]), fmaxf(s_kmax[2], s_kmax[3])), s_kmax[4]);
   const int nkk = (len + 15) >> 4;
-  constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
   constexpr uint32_t ONES = 0x3F803F80u;
-  // ldmatrix lane addressing in a [rows x 32 B] tile with the 32B swizzle (16-byte chunk ^= (row >> 2) & 1):
-  // matrix m = lane / 8, row lane % 8; every row base below is a multiple of 8, so the swizzle bit is (lane % 8) >> 2
-  const int lm = lane >> 3, lr = lane & 7, sw = lr >> 2;
-  const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * 16 + (((lm & 1) ^ sw) << 3);   // m0/m1 = dh halves of keys 0-7, m2/m3 of keys 8-15
-  const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * 16 + (((lm >> 1) ^ sw) << 3);   // m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
-  const bf16* q_lane = Qs + ((lm & 1) * 8 + lr) * 16 + (((lm >> 1) ^ sw) << 3);   // a0..a3 of the m16k16 A fragment
+  // ldmatrix lane addressing in the [rows x 128 B] tile with the 128B swizzle: matrix m = lane / 8, row lane % 8;
+  // every row base below is a multiple of 8, so the swizzle term is lane % 8
+  const int lm = lane >> 3, lr = lane & 7;
+  const bf16* k_lane = Ts + ((lm >> 1) * 8 + lr) * 64 + (((2 + (lm & 1)) ^ lr) << 3);   // m0/m1 = dh halves of keys 0-7, m2/m3 of keys 8-15
+  const bf16* v_lane = Ts + ((lm & 1) * 8 + lr) * 64 + (((4 + (lm >> 1)) ^ lr) << 3);   // m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
+  const bf16* q_lane = Ts + ((lm & 1) * 8 + lr) * 64 + (((lm >> 1) ^ lr) << 3);         // a0..a3 of the m16k16 A fragment
 #pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int row0 = warp * 32 + mt * 16;
     if (row0 >= len) break;                            // warp-uniform
     uint32_t qa[4];
-    ldmatrix_x4(qa, q_lane + row0 * 16);
+    ldmatrix_x4(qa, q_lane + row0 * 64);
     // softmax stabiliser from the Cauchy-Schwarz bound (see k_attention_bf16_short); exact row maxima as fallback
     float qn0, qn1;
     {
@@ -689,16 +686,14 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
       qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
-    float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;
-    float mb = fmaxf(row0 + g < len ? mx0 : 0.f, row0 + g + 8 < len ? mx1 : 0.f);   // query rows past the sequence do not vote
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-    if (!(mb * 0.5f < 80.f)) {                         // warp-uniform; also taken for NaN / inf inputs
+    float mx0 = sqrt_approx(qn0 * kmax2) * 1.0001f, mx1 = sqrt_approx(qn1 * kmax2) * 1.0001f;   // (2 ulp of MUFU.SQRT << the margin)
+    const bool big = !((row0 + g < len ? mx0 : 0.f) * (0.5f / QK_PRESCALE) < 80.f) || !((row0 + g + 8 < len ? mx1 : 0.f) * (0.5f / QK_PRESCALE) < 80.f);   // query rows past the sequence do not vote
+    if (__any_sync(0xffffffffu, big)) {                         // warp-uniform; also taken for NaN / inf inputs
       mx0 = -INFINITY; mx1 = -INFINITY;
 #pragma unroll 1
       for (int kk = 0; kk < nkk; ++kk) {
         uint32_t kf[4];
-        ldmatrix_x4(kf, k_lane + kk * 16 * 16);
+        ldmatrix_x4(kf, k_lane + kk * 16 * 64);
         float s0[4], s1[4];
         mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
         mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
@@ -715,20 +710,18 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     }
-    const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
+    const float nb0 = -mx0, nb1 = -mx1;               // k is pre-scaled (QK_PRESCALE): scores are base-2 exponents
     float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, ol[4] = {0.f, 0.f, 0.f, 0.f};
     auto pv_block = [&](int kk, auto mask_c) {
       constexpr bool MASK = decltype(mask_c)::value;
       uint32_t kf[4], vf[4];
-      ldmatrix_x4(kf, k_lane + kk * 16 * 16);
-      ldmatrix_x4_trans(vf, v_lane + kk * 16 * 16);
+      ldmatrix_x4(kf, k_lane + kk * 16 * 64);
+      ldmatrix_x4_trans(vf, v_lane + kk * 16 * 64);
       float s0[4], s1[4];
-      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
-      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
-      s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
-      s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
-      s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
-      s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
+      mma_bf16_16816_c(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
+      mma_bf16_16816_c(s1, qa, kf[2], kf[3], nb0, nb1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s0[i] = ex2_approx(s0[i]); s1[i] = ex2_approx(s1[i]); }
       if (MASK) {
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
@@ -877,7 +870,7 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
       if ((rc = qkv2 ? launch_qkv2_tc(h, lw, o, qb, rows, st) : launch_qkv_tc(h, lw, o, qb, rows, st))) return rc;   // norm1 + in-projection in one kernel
     } else {
       if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
-      if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b, qb, rows, 3 * D, D, false, st))) return rc;
+      if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b_hi, qb, rows, 3 * D, D, false, st))) return rc;
     }
     if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st))) return rc;
     static const bool post2 = !(getenv("RESEP_POST2") && getenv("RESEP_POST2")[0] == '0');

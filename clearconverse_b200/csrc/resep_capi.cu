@@ -113,7 +113,6 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
         float* hp = h->host_par.data() + (size_t)(b * NL + l) * POST_PAR;
         std::memcpy(hp, s.out_proj_b, D * 4); std::memcpy(hp + D, s.norm2_w, D * 4); std::memcpy(hp + 2 * D, s.norm2_b, D * 4);
         std::memcpy(hp + 3 * D, s.ffn2_b, D * 4); std::memcpy(hp + 4 * D, s.ffn1_b, FFN * 4);
-        std::memcpy(hp + 4 * D + FFN, s.in_proj_b, 3 * D * 4);
         std::memcpy(hp + 7 * D + FFN, s.norm1_w, D * 4); std::memcpy(hp + 8 * D + FFN, s.norm1_b, D * 4);
         t.h_post_par = hp;
         t.h_in_b = hp + 4 * D + FFN;
@@ -124,7 +123,22 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
       F(t.norm2_w, s.norm2_w, D); F(t.norm2_b, s.norm2_b, D);
       F(t.f1_w, s.ffn1_w, (size_t)FFN * D); F(t.f1_b, s.ffn1_b, FFN);
       F(t.f2_w, s.ffn2_w, (size_t)D * FFN); F(t.f2_b, s.ffn2_b, D);
-      Bf(t.in_w_bf, t.in_w_bl, s.in_proj_w, 3 * D * D);
+      {  // the bf16 path keeps q, k, v of a head adjacent in the qkv buffer ([head][q|k|v][16], see QKV_HEAD_STRIDE;
+         // k pre-scaled by QK_PRESCALE):
+         // a row permutation of the in-projection, so that one TMA box per (chunk, head) fetches all three slices
+        std::vector<float> pw((size_t)3 * D * D), pb(3 * D);
+        for (int part = 0; part < 3; ++part)
+          for (int hd = 0; hd < NH; ++hd)
+            for (int e = 0; e < DH; ++e) {
+              const int r_old = part * D + hd * DH + e, r_new = hd * QKV_HEAD_STRIDE + part * DH + e;
+              const float sc = part == 1 ? QK_PRESCALE : 1.f;
+              for (int c = 0; c < D; ++c) pw[(size_t)r_new * D + c] = s.in_proj_w[(size_t)r_old * D + c] * sc;
+              pb[r_new] = s.in_proj_b[r_old] * sc;
+            }
+        Bf(t.in_w_bf, t.in_w_bl, pw.data(), 3 * D * D);
+        F(t.in_b_hi, pb.data(), 3 * D);
+        std::memcpy(h->host_par.data() + (size_t)(b * NL + l) * POST_PAR + 4 * D + FFN, pb.data(), 3 * D * 4);
+      }
       Bf(t.out_w_bf, t.out_w_bl, s.out_proj_w, D * D);
       Bf(t.f1_w_bf, t.f1_w_bl, s.ffn1_w, (size_t)FFN * D);
       Bf(t.f2_w_bf, t.f2_w_bl, s.ffn2_w, (size_t)D * FFN);

@@ -19,6 +19,11 @@ constexpr int STRIDE = 8;
 constexpr int CHUNK = 150;   // segment_size K
 constexpr int NH = 8;
 constexpr int DH = 16;
+// bf16 qkv buffer: row = [head 0: q16 k16 v16 | head 1: ... ] (the fp32 / tf32 paths keep torch's [q128 | k128 | v128])
+constexpr int QKV_HEAD_STRIDE = 3 * DH, QKV_K = DH, QKV_V = 2 * DH;
+// ... and its k slice is pre-multiplied (in the fp32 in-projection weights / bias, before the bf16 split) by
+// 1/sqrt(DH) * log2(e): q . k is then the softmax exponent in base 2 and the attention kernels need no scaling FFMA
+constexpr float QK_PRESCALE = 0.25f * 1.4426950408889634f;
 constexpr int FFN = 1024;
 constexpr int NL = 8;
 constexpr int NSPK = 2;
@@ -29,14 +34,15 @@ typedef __nv_bfloat16 bf16;
 
 struct LayerDev {
   const float *norm1_w, *norm1_b, *in_w, *in_b, *out_w, *out_b, *norm2_w, *norm2_b, *f1_w, *f1_b, *f2_w, *f2_b;
-  const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;       // bf16 copies (RESEP_PREC_BF16)
+  const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;       // bf16 copies (RESEP_PREC_BF16); in_w_bf / in_w_bl rows head-interleaved
+  const float* in_b_hi;                                     // in_b in the same head-interleaved order
   const bf16 *in_w_bl, *out_w_bl, *f1_w_bl, *f2_w_bl;       // bf16(W - bf16(W)): low part for the split-weight mode
   const float *in_w_tf, *out_w_tf, *f1_w_tf, *f2_w_tf;      // tf32-rounded fp32 copies (RESEP_PREC_TF32): hi part
   const float *in_w_lo, *out_w_lo, *f1_w_lo, *f2_w_lo;      // tf32(W - hi): the TF32 mode runs W = hi + lo
   // HOST copy of out_b[128], norm2_w[128], norm2_b[128], f2_b[128], f1_b[1024]: k_post2_tc takes them as kernel
   // parameters (constant bank) so that its epilogues do not spend shared-memory bandwidth on broadcast loads
   const float* h_post_par;
-  const float* h_in_b;      // HOST copy of in_b[384], norm1_w[128], norm1_b[128] (k_qkv2_tc kernel parameters)
+  const float* h_in_b;      // HOST copy of in_b_hi[384], norm1_w[128], norm1_b[128] (k_qkv2_tc kernel parameters)
 };
 struct BlockDev {
   LayerDev layers[NL];

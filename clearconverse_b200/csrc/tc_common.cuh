@@ -36,10 +36,10 @@ static int make_tmap(ResepHandle* h, CUtensorMap* m, const T* base, int64_t rows
 static int make_tmap_head(ResepHandle* h, CUtensorMap* m, const bf16* base, int64_t rows, int cols, int box_rows) {
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(bf16)};
-  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};   // q | k | v of one head (48 columns) + 16 unused
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(h, RESEP_ECUDA, "cuTensorMapEncodeTiled (head slice) failed: " + std::to_string((int)r));
   return RESEP_OK;
