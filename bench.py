@@ -90,6 +90,8 @@ def kernel_work(name: str, batch: int, t: int):
         return "hbm", 2 * rows * (512 + 256)
     if name.startswith("k_block_epilogue"):
         return "hbm", (2 * M + chunks) * 128 * 4 * 4
+    if name.startswith("k_maskdec"):                   # fused output_fc + mask + decoder: PReLU bf16 + features in, samples out
+        return "hbm", M * (256 + 512) + batch * t * 8
     if name.startswith("k_decoder"):
         return "hbm", batch * L * (256 + 128) * 4 + batch * t * 8
     if name.startswith("k_encoder"):

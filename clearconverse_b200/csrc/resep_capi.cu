@@ -205,6 +205,10 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
   }
   p->n_chunks = chunks;
   p->M = chunks * CHUNK;
+  p->maskdec_ok = true;
+  for (int i = 0; i < B; ++i) {
+    if (8LL * CHUNK * item_S[i] < item_len[i] || item_off[i] + item_len[i] >= (1LL << 30)) p->maskdec_ok = false;
+  }
   std::vector<int> chunk_item(chunks), chunk_frame0(chunks), mem_pos(chunks);
   std::vector<int> mem_seq_off;
   {
@@ -500,6 +504,8 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     if ((rc = launch_prelu(h, ws.a, h->w.prelu_a, ws.y, p->M * D, st))) return rc;
     if ((rc = launch_gemm_f32(h, ws.y, h->w.fc_w, h->w.fc_b, nullptr, mask, p->M, NSPK * D, D, true, st))) return rc;
   } else {
+    static const bool use_maskdec = !(getenv("RESEP_MASKDEC") && getenv("RESEP_MASKDEC")[0] == '0');
+    if (prelu_out && p->maskdec_ok && use_maskdec) return launch_maskdec(h, prelu_out, ws.x0, *p, est, st);
     float* y_mask = prelu_out ? reinterpret_cast<float*>(prelu_out) : ws.y;
     if ((rc = tc_run_mask(h, ws.a, y_mask, mask, p->M, precision, st, prelu_out != nullptr))) return rc;
   }

@@ -66,6 +66,9 @@ struct Plan {
   int max_mem_len = 0;
   int n_mem_tiles = 0;    // attention query tiles over the memory sequences
   int n_dec_tiles = 0;
+  // k_maskdec_tc (fused output_fc + decoder) needs a token row for every output slot of every item (8 * 150 * S >= T:
+  // false only when L % 150 == 149 and T % 8 != 0) and sample offsets that fit an int
+  bool maskdec_ok = false;
   // one device allocation holding every table below
   void* dev = nullptr;
   size_t dev_bytes = 0;
@@ -183,6 +186,8 @@ template <typename OutT>
 int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st);
 // mask [M,256] (already relu'd), x0 [M,128] -> est
 int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Plan& p, float* est, cudaStream_t st);
+// bf16 mode: output_fc + ReLU mask + feature product + decoder in one kernel (kernels_maskdec.cu); needs p.maskdec_ok
+int launch_maskdec(ResepHandle* h, const bf16* prelu, const float* x0, const Plan& p, float* est, cudaStream_t st);
 
 // ---------------------------------------------------------------- tensor-core kernels (kernels_tc.cu)
 int tc_init(ResepHandle* h);

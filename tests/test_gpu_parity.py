@@ -335,3 +335,32 @@ def test_sliced_intra_blocks_match_unsliced(sds, cuda_lib_built):
                 outs[(prec, sl)] = torch.load(path)
     for prec in ("fp32", "bf16"):
         assert torch.equal(outs[(prec, "378")], outs[(prec, "0")]) and torch.equal(outs[(prec, "100")], outs[(prec, "0")])
+
+
+def test_fused_mask_decoder_matches_unfused(sds, cuda_lib_built):
+    """bf16 mode: k_maskdec_tc (output_fc + ReLU mask + feature product + decoder + overlap-add in one kernel) against
+    the unfused mask GEMM + k_decoder (RESEP_MASKDEC=0, subprocess).  Same MMA order, same fp32 FMA order over the
+    filters: the waveforms must agree to the last bit.  Ragged lengths cover T % 8 != 0, single-frame items, and an
+    item with L % 150 == 149 and T % 8 != 0 (no token row for its last slot: the whole batch takes the unfused path)."""
+    import subprocess, sys, tempfile
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from clearconverse_b200 import SepformerSeparation, synth, weights\n"
+        "sep = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision='bf16', batch_mode='independent')\n"
+        "outs = {}\n"
+        "for name, lens in (('ragged', [32000, 16, 1211, 4000, 9000, 1208, 23, 8191]), ('fallback', [1203, 4000]), ('one', [2000])):\n"
+        "    segs = [synth.synth_mixture(n, 40 + i)[0] for i, n in enumerate(lens)]\n"
+        "    outs[name] = [o.cpu() for o in sep.separate_segments(segs)]\n"
+        "sepc = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision='bf16', batch_mode='coupled')\n"
+        "outs['coupled'] = [sepc.separate_batch(synth.synth_batch(3, 12001, 5)).cpu()]\n"
+        "torch.save(outs, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("1", "0"):
+            path = os.path.join(d, f"md_{flag}.pt")
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, RESEP_MASKDEC=flag))
+            res[flag] = torch.load(path)
+    for name in res["1"]:
+        for got, want in zip(res["1"][name], res["0"][name]):
+            assert got.shape == want.shape and torch.isfinite(got).all()
+            assert torch.equal(got, want), f"{name}: max diff {(got - want).abs().max().item():.3e}"
