@@ -29,9 +29,9 @@ constexpr int THREADS = 224;
 constexpr int ROWS_OUT = 127;                    // output slots per tile (tile = 128 rows, first row is the halo)
 constexpr int WHALF = 256 * 128;                 // [256 rows x 128 B]: one K half of Wfc (hi or lo)
 constexpr int OFF_W = 0;                         // hi k0, hi k1, lo k0, lo k1
-constexpr int NA = 3, ABOX = 128 * 128;          // A ring: [128 rows x 64 bf16] K halves
+constexpr int NA = 2, ABOX = 128 * 128;          // A ring: [128 rows x 64 bf16] K halves (one tile)
 constexpr int OFF_A = OFF_W + 4 * WHALF;
-constexpr int NX = 2, XBOX = 128 * 128;          // feature ring: [128 rows x 32 fp32]
+constexpr int NX = 3, XBOX = 128 * 128;          // feature ring: [128 rows x 32 fp32]
 constexpr int OFF_X = OFF_A + NA * ABOX;
 constexpr int OFF_DW = OFF_X + NX * XBOX;        // decoder filters fp32 [128][16]
 constexpr int OFF_B = OFF_DW + D * KSZ * 4;      // output_fc bias fp32 [256] (channel = 2 * filter + speaker)
@@ -89,12 +89,15 @@ k_maskdec_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  if (warp >= 3) {   // static parameters (not produced by the previous kernel)
+  if (warp >= 3) {   // static parameters (not produced by the previous kernel): all loads in flight before the stores
     const int t = threadIdx.x - 96;
-    float* dw = reinterpret_cast<float*>(smem + OFF_DW);
-    float* bs = reinterpret_cast<float*>(smem + OFF_B);
-    for (int i = t; i < D * KSZ; i += 128) dw[i] = __ldg(a.dec_w + i);
-    for (int i = t; i < NSPK * D; i += 128) bs[i] = __ldg(a.fc_b + i);
+    float4* dw4 = reinterpret_cast<float4*>(smem + OFF_DW);
+    float4* bs4 = reinterpret_cast<float4*>(smem + OFF_B);
+    const float4* gdw = reinterpret_cast<const float4*>(a.dec_w);
+    const float4 w0 = __ldg(gdw + t), w1 = __ldg(gdw + t + 128), w2 = __ldg(gdw + t + 256), w3 = __ldg(gdw + t + 384);
+    const float4 b4 = t < NSPK * D / 4 ? __ldg(reinterpret_cast<const float4*>(a.fc_b) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dw4[t] = w0; dw4[t + 128] = w1; dw4[t + 256] = w2; dw4[t + 384] = w3;
+    if (t < NSPK * D / 4) bs4[t] = b4;
   }
   tc_fence_before();
   __syncthreads();

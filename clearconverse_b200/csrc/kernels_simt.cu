@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* 
                                                                    float* __restrict__ seq_mean, int seq_len,
                                                                    bf16* __restrict__ prelu_out, const float* __restrict__ prelu_a) {
   extern __shared__ __align__(16) float ys[];            // [seq_len][128]
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL successor (k_maskdec_tc) may set up meanwhile
   __shared__ double red[2][EPI_T / 32];
   __shared__ float stat[2];
   __shared__ __align__(16) float colsum[EPI_T / 32][D];

@@ -32,14 +32,26 @@ def si_snr_db(est: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     return 10 * torch.log10(proj.pow(2).sum(-1) / (noise.pow(2).sum(-1) + 1e-20))
 
 
-def si_snr_delta(est: torch.Tensor, oracle_est: torch.Tensor, mix: torch.Tensor) -> float:
+MIN_REF_SI_SNR_DB = -20.0   # SI-SNR deltas are evaluated where the oracle's own SI-SNR is at least this
+MIN_EST_VS_EST_DB = 45.0    # weight-independent bf16 gate: error at least 45 dB below the oracle's estimate
+
+
+def si_snr_delta(est: torch.Tensor, oracle_est: torch.Tensor, mix: torch.Tensor, min_ref_db: float = MIN_REF_SI_SNR_DB) -> float:
     """The bf16 acceptance metric.  With random-init weights SI-SNR against the true sources
     sits near -38 dB where it is ill-conditioned, so the delta is taken
     against a reference the estimates actually resemble: the mixture.  delta =
-    max over (item, speaker) of |SI-SNR(est, mix) - SI-SNR(oracle_est, mix)| in dB."""
+    max over (item, speaker) of |SI-SNR(est, mix) - SI-SNR(oracle_est, mix)| in dB, over the pairs whose oracle
+    SI-SNR is >= min_ref_db.  A perturbation S dB below the estimate can move an SI-SNR of R dB by up to
+    20 log10(1 + 10^((|R| - S) / 20)): for R -> -inf (estimate orthogonal to the reference) any perturbation
+    moves it arbitrarily.  Measured with four weight seeds (scripts/gpu_fc_probe.py): S = 49.8 ... 52.9 dB
+    everywhere; delta <= 0.043 dB for R >= -22 dB, 0.05-0.08 around -25 ... -31 dB, 0.15-1.3 dB below -45 dB.  A
+    trained separator sits at R >> 0 dB.  The pairs left out here are still held to MIN_EST_VS_EST_DB."""
     a = si_snr_db(est.permute(0, 2, 1), mix[:, None, :])
     b = si_snr_db(oracle_est.permute(0, 2, 1), mix[:, None, :])
-    return (a - b).abs().max().item()
+    ok = b >= min_ref_db
+    if not ok.any():
+        return 0.0
+    return (a - b).abs()[ok].max().item()
 
 
 @pytest.fixture(scope="module")
@@ -235,7 +247,26 @@ def test_bf16_forward_within_spec(make_sep, oracle, B, T, seed):
     got = sep.separate_batch(mix).cpu()
     assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
     assert si_snr_delta(got, want, mix) <= 0.05
-    assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > 35.0   # est vs fp32 est
+    assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB   # est vs fp32 est
+
+
+@pytest.mark.parametrize("wseed", [1, 2, 3])
+def test_bf16_other_weight_seeds(cuda_lib_built, wseed):
+    """The bf16 gates with other random weights than the module-wide seed 0 (seeds 1 and 3 produce speakers nearly
+    orthogonal to the mixture, where only the est-vs-est gate is meaningful)."""
+    from clearconverse_b200 import SepformerSeparation
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    oracle = OracleSepformerSeparation(seed=wseed)
+    sep = SepformerSeparation(oracle.component_state_dicts(), device="cuda:0", precision="bf16", batch_mode="coupled")
+    try:
+        for mix in (synth_batch(2, 2000, 2), synth_batch(3, 9000, 5)):
+            want = oracle.separate_batch(mix)
+            got = sep.separate_batch(mix).cpu()
+            assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
+            assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB
+            assert si_snr_delta(got, want, mix) <= 0.05
+    finally:
+        sep.close()
 
 
 # ------------------------------------------------------------------ BASELINE.json full sizes
@@ -248,6 +279,7 @@ def test_config2_full_size_all_modes(make_sep, oracle):
         assert (got - want).abs().max().item() <= tol, prec
     got = make_sep("bf16", "coupled").separate_batch(mix).cpu()
     assert si_snr_delta(got, want, mix) <= 0.05
+    assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB
 
 
 def test_config3_long_sequence_properties(make_sep, oracle):
@@ -312,7 +344,7 @@ def test_bf16_ragged_independent_segments(make_sep, oracle):
         assert got.shape == want.shape and torch.isfinite(got).all()
         assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
         if s.numel() >= 1000:
-            assert si_snr_db(got.T[None], want.T[None]).min().item() > 35.0
+            assert si_snr_db(got.T[None], want.T[None]).min().item() > MIN_EST_VS_EST_DB
 
 
 def test_sliced_intra_blocks_match_unsliced(sds, cuda_lib_built):
