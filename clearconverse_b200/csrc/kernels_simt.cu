@@ -474,12 +474,31 @@ __global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* 
   const int64_t off = (int64_t)seq * seq_len;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 w4 = reinterpret_cast<const float4*>(fn_w)[lane], b4 = reinterpret_cast<const float4*>(fn_b)[lane];
+  // Each warp owns rows warp, warp + 16, ...: up to RPW of them.  All their loads are issued before the first one is
+  // used (a row at a time the kernel was latency-bound at 15 us per CTA), and the skip-connection rows are fetched
+  // while the chunk statistics are being reduced.
+  constexpr int RPW = (CHUNK + NW_ - 1) / NW_;
   double s1 = 0.0, s2 = 0.0;
-  for (int r = warp; r < seq_len; r += NW_) {
-    float4 y = ln_row(reinterpret_cast<const float4*>(o + (off + r) * D)[lane], w4, b4);
-    reinterpret_cast<float4*>(ys + r * D)[lane] = y;
-    s1 += (double)y.x + (double)y.y + (double)y.z + (double)y.w;
-    s2 += (double)y.x * y.x + (double)y.y * y.y + (double)y.z * y.z + (double)y.w * y.w;
+  float4 xr[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + i * NW_;
+    if (r < seq_len) xr[i] = reinterpret_cast<const float4*>(o + (off + r) * D)[lane];
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + i * NW_;
+    if (r < seq_len) {
+      const float4 y = ln_row(xr[i], w4, b4);
+      reinterpret_cast<float4*>(ys + r * D)[lane] = y;
+      s1 += (double)y.x + (double)y.y + (double)y.z + (double)y.w;
+      s2 += (double)y.x * y.x + (double)y.y * y.y + (double)y.z * y.z + (double)y.w * y.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + i * NW_;
+    if (r < seq_len) xr[i] = reinterpret_cast<const float4*>(xin)[(off + r) * (D / 4) + lane];
   }
   s1 = warp_sum_d(s1);
   s2 = warp_sum_d(s2);
@@ -500,10 +519,13 @@ __global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* 
   const float4 g4 = reinterpret_cast<const float4*>(gln_w)[lane], h4 = reinterpret_cast<const float4*>(gln_b)[lane];
   const float slope = prelu_out != nullptr ? prelu_a[0] : 0.f;
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = warp; r < seq_len; r += NW_) {
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + i * NW_;
+    if (r >= seq_len) continue;
     const int64_t idx = (off + r) * (D / 4) + lane;
     const float4 y = reinterpret_cast<const float4*>(ys + r * D)[lane];
-    const float4 x = reinterpret_cast<const float4*>(xin)[idx];
+    const float4 x = xr[i];
     float4 v;
     v.x = g4.x * (y.x - mu) * rstd + h4.x + x.x;
     v.y = g4.y * (y.y - mu) * rstd + h4.y + x.y;
