@@ -694,4 +694,66 @@ int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Pla
   return RESEP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-source peak normalisation s / (max|s| + 1e-8), the first thing the caller does with every separated source
+// (api.py:1082): two passes over est on the device instead of a device->host round trip per source.
+constexpr int PEAK_TILE = 4096;   // samples per CTA
+__global__ void __launch_bounds__(256) k_peak_max(const float* __restrict__ est, const int64_t* __restrict__ item_off,
+                                                  const int64_t* __restrict__ item_len, unsigned* __restrict__ peaks) {
+  const int item = blockIdx.y;
+  const int64_t T = item_len[item];
+  const int64_t t0 = (int64_t)blockIdx.x * PEAK_TILE;
+  if (t0 >= T) return;
+  const float2* src = reinterpret_cast<const float2*>(est) + item_off[item];
+  const int64_t t1 = t0 + PEAK_TILE < T ? t0 + PEAK_TILE : T;
+  float m0 = 0.f, m1 = 0.f;
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) {
+    const float2 v = src[t];
+    m0 = fmaxf(m0, fabsf(v.x));
+    m1 = fmaxf(m1, fabsf(v.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(peaks + 2 * item, __float_as_uint(m0));
+    atomicMax(peaks + 2 * item + 1, __float_as_uint(m1));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_peak_scale(float* __restrict__ est, const int64_t* __restrict__ item_off,
+                                                    const int64_t* __restrict__ item_len, const float* __restrict__ peaks) {
+  const int item = blockIdx.y;
+  const int64_t T = item_len[item];
+  const int64_t t0 = (int64_t)blockIdx.x * PEAK_TILE;
+  if (t0 >= T) return;
+  float2* dst = reinterpret_cast<float2*>(est) + item_off[item];
+  const int64_t t1 = t0 + PEAK_TILE < T ? t0 + PEAK_TILE : T;
+  const float d0 = peaks[2 * item] + 1e-8f, d1 = peaks[2 * item + 1] + 1e-8f;
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) {
+    float2 v = dst[t];
+    v.x = v.x / d0;                                   // IEEE division: bit-identical to the caller's torch expression
+    v.y = v.y / d1;
+    dst[t] = v;
+  }
+}
+
+int launch_peak_normalize(ResepHandle* h, float* est, const Plan& p, int64_t max_len, float* peaks, cudaStream_t st) {
+  if (p.B == 0 || max_len <= 0) return RESEP_OK;
+  RESEP_CUDA(h, cudaMemsetAsync(peaks, 0, sizeof(float) * 2 * p.B, st));
+  const dim3 grid((unsigned)((max_len + PEAK_TILE - 1) / PEAK_TILE), (unsigned)p.B);
+  {
+    ProfScope prof_scope(h, "k_peak_max", st);
+    k_peak_max<<<grid, 256, 0, st>>>(est, p.d_item_off, p.d_item_len, reinterpret_cast<unsigned*>(peaks));
+    RESEP_LAUNCH_CHECK(h, "k_peak_max");
+  }
+  ProfScope prof_scope(h, "k_peak_scale", st);
+  k_peak_scale<<<grid, 256, 0, st>>>(est, p.d_item_off, p.d_item_len, peaks);
+  RESEP_LAUNCH_CHECK(h, "k_peak_scale");
+  return RESEP_OK;
+}
+
 }  // namespace resep

@@ -654,6 +654,26 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                       static_cast<cudaStream_t>(stream), nullptr);
 }
 
+int resep_peak_normalize(ResepHandle* h, float* est, const int64_t* item_off, const int64_t* item_len, int B, float* peaks,
+                         void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!est || !item_off || !item_len || !peaks || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or empty batch");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan* p = nullptr;
+  for (Plan* q : h->plans) {                          // the forward that produced est left a plan with these offsets
+    if (q->B != B || q->key.size() != 2 + 2 * (size_t)B) continue;
+    bool same = true;
+    for (int i = 0; i < B && same; ++i) same = q->key[2 + 2 * i] == item_off[i] && q->key[3 + 2 * i] == item_len[i];
+    if (same) { p = q; break; }
+  }
+  int rc;
+  if (!p && (rc = get_plan(h, B, item_off, item_len, RESEP_BATCH_INDEPENDENT, st, &p))) return rc;
+  int64_t max_len = 0;
+  for (int i = 0; i < B; ++i) max_len = item_len[i] > max_len ? item_len[i] : max_len;
+  return launch_peak_normalize(h, est, *p, max_len, peaks, st);
+}
+
 int resep_forward_debug(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
                         float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode, void* stream,
                         const ResepDebugOut* dbg) {

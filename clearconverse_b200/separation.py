@@ -121,6 +121,17 @@ class _Engine:
             _lib.check(self.lib, self.handle, rc)
         return est
 
+    def peak_normalize(self, est_flat: torch.Tensor, offs: list[int], lens: list[int]) -> torch.Tensor:
+        """In place: every (item, speaker) source of est_flat divided by its max |.| + 1e-8 (api.py:1082).
+        Returns the maxima, [B, n_spk] on the device."""
+        B = len(lens)
+        peaks = torch.empty(B, NUM_SPKS, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.resep_peak_normalize(self.handle, est_flat.data_ptr(), (C.c_int64 * B)(*offs), (C.c_int64 * B)(*lens),
+                                               B, peaks.data_ptr(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(self.lib, self.handle, rc)
+        return peaks
+
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
             self.lib.resep_destroy(self.handle)
@@ -304,21 +315,26 @@ class SepformerSeparation:
                                "Kernel size can't be greater than actual input size")
 
     @torch.no_grad()
-    def separate_batch(self, mix: torch.Tensor) -> torch.Tensor:
-        """mix [B,T] float32 (any device) -> est_sources [B,T,n_spk] float32 on ``self.device``."""
+    def separate_batch(self, mix: torch.Tensor, peak_normalize: bool = False) -> torch.Tensor:
+        """mix [B,T] float32 (any device) -> est_sources [B,T,n_spk] float32 on ``self.device``.
+        ``peak_normalize=True`` additionally applies the caller's `source / (source.abs().max() + 1e-8)`
+        (api.py:1082) to every (item, speaker) source on the device."""
         self._check_mix(mix)
         B, T = mix.shape
         mix = mix.to(self.device).contiguous()
+        offs, lens = [b * T for b in range(B)], [T] * B
         est = torch.ops.clearconverse_b200.resep_separate(
-            mix.view(-1), [b * T for b in range(B)], [T] * B, self._engine.id,
+            mix.view(-1), offs, lens, self._engine.id,
             _lib.PRECISIONS[self.precision], _lib.BATCH_MODES[self.batch_mode])
+        if peak_normalize:
+            self._engine.peak_normalize(est, offs, lens)
         return est.view(B, T, NUM_SPKS)
 
     forward = separate_batch
     __call__ = separate_batch
 
     @torch.no_grad()
-    def separate_segments(self, segments: list[torch.Tensor]) -> list[torch.Tensor]:
+    def separate_segments(self, segments: list[torch.Tensor], peak_normalize: bool = False) -> list[torch.Tensor]:
         """Ragged batch: 1-D (or [1,T]) float32 segments of different lengths in ONE launch
         sequence, each separated independently (== one ``separate_batch`` call per segment, the
         way api.py:1073-1077 loops).  Returns a list of [T_i, n_spk] tensors on ``self.device``."""
@@ -337,7 +353,21 @@ class SepformerSeparation:
             return []
         est = torch.ops.clearconverse_b200.resep_separate(
             torch.cat(flat), offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT)
+        if peak_normalize:
+            self._engine.peak_normalize(est, offs, lens)
         return [est[2 * o:2 * (o + n)].view(n, NUM_SPKS) for o, n in zip(offs, lens)]
+
+    @torch.no_grad()
+    def separate_regions(self, audio: torch.Tensor, spans: list[tuple[int, int]], peak_normalize: bool = False) -> list[torch.Tensor]:
+        """The batched overlap driver: ``audio`` is one file's waveform ([T] or [1,T]),
+        ``spans`` the (start, end) sample ranges of its overlap regions in the caller's order -- what api.py:1073-1077
+        slices one at a time.  Identical spans (two speakers' segments over the same overlap, api.py:1387-1394) are
+        separated once.  Returns one [T_i, n_spk] tensor per span (duplicates share storage)."""
+        from .sharding import dedupe_spans
+        audio = audio.reshape(-1)
+        unique, inverse = dedupe_spans(spans)
+        outs = self.separate_segments([audio[a:b] for a, b in unique], peak_normalize=peak_normalize)
+        return [outs[i] for i in inverse]
 
     @torch.no_grad()
     def separate_stream(self, batches, out_buffers=None, depth: int = 2):

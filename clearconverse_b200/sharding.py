@@ -18,6 +18,18 @@ FLOP_MEM_CHUNK_BASE = 8 * 655_360          # memory transformer, per chunk, GEMM
 FLOP_MEM_CHUNK_PER_SEQ = 8 * 512           # ... attention part, per chunk per sequence element
 
 
+def dedupe_spans(spans):
+    """(start, end) sample ranges -> (unique ranges in first-seen order, index of each input range in that list)."""
+    seen, unique, inverse = {}, [], []
+    for a, b in spans:
+        key = (int(a), int(b))
+        if key not in seen:
+            seen[key] = len(unique)
+            unique.append(key)
+        inverse.append(seen[key])
+    return unique, inverse
+
+
 def frames_of(T: int) -> int:
     return (T - KSZ) // STRIDE + 1
 

@@ -133,6 +133,14 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                   float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                   void* stream);
 
+/* Replaces the caller's first step on every separated source, api.py:1082
+ * `source / (source.abs().max() + 1e-8)`, on the device and for all items at once:
+ *   est[item][t][spk] /= max_t |est[item][t][spk]| + 1e-8   in place, layout as resep_forward's est
+ *   peaks        DEVICE fp32[2*B], receives the maxima (item-major, speaker-minor)
+ * IEEE division, so the result equals the torch expression bit for bit.  NaN samples are ignored by the maximum. */
+int resep_peak_normalize(ResepHandle* h, float* est, const int64_t* item_off, const int64_t* item_len, int B,
+                         float* peaks, void* stream);
+
 /* Same as resep_forward, additionally copying intermediates for per-kernel parity tests.
  * Any pointer may be NULL.  Token-major fp32, chunk-padded: M = 150 * sum_i S_i rows of 128. */
 typedef struct ResepDebugOut {

@@ -396,3 +396,36 @@ def test_fused_mask_decoder_matches_unfused(sds, cuda_lib_built):
         for got, want in zip(res["1"][name], res["0"][name]):
             assert got.shape == want.shape and torch.isfinite(got).all()
             assert torch.equal(got, want), f"{name}: max diff {(got - want).abs().max().item():.3e}"
+
+
+# ------------------------------------------------------------------ the ops either side of the path
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_peak_normalize_matches_caller_expression(make_sep, prec):
+    """api.py:1082 `source / (source.abs().max() + 1e-8)` per (item, speaker), done on the device: bit-identical to the
+    torch expression applied to the un-normalised output (IEEE division), dense and ragged batches."""
+    sep = make_sep(prec, "coupled")
+    mix = synth_batch(3, 9000, 5)
+    plain = sep.separate_batch(mix)
+    got = sep.separate_batch(mix, peak_normalize=True)
+    want = plain / (plain.abs().amax(dim=1, keepdim=True) + 1e-8)
+    assert torch.equal(got, want)
+    assert abs(got.abs().amax(dim=1).max().item() - 1.0) < 1e-6
+    segs = [synth_mixture(n, 90 + i)[0] for i, n in enumerate([16, 5000, 1211, 20000])]
+    plain_r = sep.separate_segments(segs)
+    got_r = sep.separate_segments(segs, peak_normalize=True)
+    for g, p in zip(got_r, plain_r):
+        assert torch.equal(g, p / (p.abs().amax(dim=0, keepdim=True) + 1e-8))
+
+
+def test_separate_regions_dedupes_and_matches_per_region_calls(make_sep):
+    """The batched overlap driver: regions of one file, duplicates separated once, each result identical to the
+    reference's own way of doing it (one B=1 separate_batch call per sliced region, api.py:1073-1077)."""
+    sep = make_sep("fp32", "independent")
+    audio = synth_mixture(40000, 123)[0]
+    spans = [(1000, 9000), (12000, 12016), (1000, 9000), (20000, 39999), (5000, 6211)]
+    outs = sep.separate_regions(audio, spans)
+    assert outs[0].data_ptr() == outs[2].data_ptr()                      # separated once
+    for (a, b), o in zip(spans, outs):
+        want = sep.separate_batch(audio[a:b][None])[0]
+        assert o.shape == (b - a, 2)
+        assert (o - want).abs().max().item() <= 1e-6

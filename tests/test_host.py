@@ -96,6 +96,15 @@ def test_flops_match_survey_figures():
     assert sharding.chunks_of(32000) == 27 and sharding.chunks_of(480000) == 400 and sharding.chunks_of(16 + 8 * 149) == 2
 
 
+def test_dedupe_spans_keeps_order_and_maps_back():
+    from clearconverse_b200.sharding import dedupe_spans
+    spans = [(100, 900), (0, 50), (100, 900), (100, 901), (0, 50)]
+    unique, inverse = dedupe_spans(spans)
+    assert unique == [(100, 900), (0, 50), (100, 901)]
+    assert [unique[i] for i in inverse] == spans
+    assert dedupe_spans([]) == ([], [])
+
+
 def test_bucketing_and_assignment_cover_everything_once():
     lens = synth.meeting_overlap_segments(720.0)
     for ws in (1, 2, 4, 8):
