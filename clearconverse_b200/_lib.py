@@ -57,6 +57,8 @@ SYMBOLS = {
     "resep_workspace_bytes": (C.c_int, [_H, C.c_int, _i64p, C.c_int, C.POINTER(C.c_size_t)]),
     "resep_forward": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                 C.c_int, C.c_int, C.c_void_p]),
+    "resep_resample_fir": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_void_p]),
     "resep_peak_normalize": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p]),
     "resep_forward_debug": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_int, C.c_int, C.c_void_p, C.POINTER(ResepDebugOut)]),

@@ -756,4 +756,53 @@ int launch_peak_normalize(ResepHandle* h, float* est, const Plan& p, int64_t max
   return RESEP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Polyphase FIR resampler (windowed-sinc taps computed by the host layer: torchaudio.functional.resample's
+// definition).  The product feeds 16 kHz audio to a separator trained at 8 kHz (api.py:115 vs the model's
+// sample_rate 8000) without resampling; these two passes let a caller run the model at its native rate and get the
+// sources back at the file's rate without leaving the device.
+//   y[row][m * up + p][c] = sum_j taps[p][j] * xpad[row][m * down + j][c],  xpad[i] = x[i - width] (0 outside)
+// x: [rows][n_in][ch], y: [rows][n_out][ch] (ch = 1 for mixtures, 2 for separated sources); taps in shared memory.
+__global__ void __launch_bounds__(256) k_resample_fir(const float* __restrict__ x, int64_t n_in, float* __restrict__ y, int64_t n_out,
+                                                      int ch, int down, int up, const float* __restrict__ taps, int ktaps, int width) {
+  extern __shared__ float s_taps[];
+  const bool in_smem = (size_t)up * ktaps * sizeof(float) <= 48 * 1024;   // else (e.g. 44.1 kHz -> 8 kHz: 80 x 509) from L1/L2
+  if (in_smem) {
+    for (int i = threadIdx.x; i < up * ktaps; i += 256) s_taps[i] = taps[i];
+    __syncthreads();
+  }
+  const int row = blockIdx.y;
+  const float* xr = x + (int64_t)row * n_in * ch;
+  float* yr = y + (int64_t)row * n_out * ch;
+  const int64_t total = n_out * ch;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int64_t o = e / ch;
+    const int c = (int)(e - o * ch);
+    const int64_t m = o / up;
+    const int p = (int)(o - m * up);
+    const int64_t i0 = m * down - width;
+    const float* tp = (in_smem ? s_taps : taps) + p * ktaps;
+    float acc = 0.f;
+    for (int j = 0; j < ktaps; ++j) {
+      const int64_t i = i0 + j;
+      if (i >= 0 && i < n_in) acc = fmaf(tp[j], xr[i * ch + c], acc);
+    }
+    yr[e] = acc;
+  }
+}
+
+int launch_resample_fir(ResepHandle* h, const float* x, int rows, int64_t n_in, float* y, int64_t n_out, int ch, int down, int up,
+                        const float* taps, int ktaps, int width, cudaStream_t st) {
+  if (rows <= 0 || n_out <= 0) return RESEP_OK;
+  const size_t tap_bytes = (size_t)up * ktaps * sizeof(float);
+  const size_t smem = tap_bytes <= 48 * 1024 ? tap_bytes : 0;
+  int64_t blocks = (n_out * ch + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  ProfScope prof_scope(h, "k_resample_fir", st);
+  k_resample_fir<<<dim3((unsigned)blocks, (unsigned)rows), 256, smem, st>>>(x, n_in, y, n_out, ch, down, up,
+                                                                                                       taps, ktaps, width);
+  RESEP_LAUNCH_CHECK(h, "k_resample_fir");
+  return RESEP_OK;
+}
+
 }  // namespace resep

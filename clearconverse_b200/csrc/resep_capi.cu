@@ -654,6 +654,15 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                       static_cast<cudaStream_t>(stream), nullptr);
 }
 
+int resep_resample_fir(ResepHandle* h, const float* x, int rows, int64_t n_in, float* y, int64_t n_out, int channels, int down,
+                       int up, const float* taps, int ktaps, int width, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!x || !y || !taps || rows < 0 || n_in < 0 || n_out < 0 || channels < 1 || down < 1 || up < 1 || ktaps < 1 || width < 0)
+    return set_err(h, RESEP_EINVAL, "resample: bad argument");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  return launch_resample_fir(h, x, rows, n_in, y, n_out, channels, down, up, taps, ktaps, width, static_cast<cudaStream_t>(stream));
+}
+
 int resep_peak_normalize(ResepHandle* h, float* est, const int64_t* item_off, const int64_t* item_len, int B, float* peaks,
                          void* stream) {
   if (!h) return RESEP_EINVAL;

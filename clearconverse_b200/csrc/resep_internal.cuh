@@ -186,6 +186,8 @@ template <typename OutT>
 int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int64_t n, cudaStream_t st);
 // mask [M,256] (already relu'd), x0 [M,128] -> est
 int launch_decoder(ResepHandle* h, const float* mask, const float* x0, const Plan& p, float* est, cudaStream_t st);
+int launch_resample_fir(ResepHandle* h, const float* x, int rows, int64_t n_in, float* y, int64_t n_out, int ch, int down, int up,
+                        const float* taps, int ktaps, int width, cudaStream_t st);
 // est[item][t][spk] /= max_t |est[item][t][spk]| + 1e-8 (api.py:1082); peaks: device float[2 * B], receives the maxima
 int launch_peak_normalize(ResepHandle* h, float* est, const Plan& p, int64_t max_len, float* peaks, cudaStream_t st);
 // bf16 mode: output_fc + ReLU mask + feature product + decoder in one kernel (kernels_maskdec.cu); needs p.maskdec_ok

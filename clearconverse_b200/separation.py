@@ -121,6 +121,24 @@ class _Engine:
             _lib.check(self.lib, self.handle, rc)
         return est
 
+    def resample(self, x: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+        """x [rows, n, channels] fp32 on the device -> [rows, ceil(n * new / orig), channels]; torchaudio.functional.resample's
+        arithmetic (its zero padding included) as one FIR pass on the device."""
+        key = (int(orig_freq), int(new_freq))
+        cache = self.__dict__.setdefault("_taps", {})
+        if key not in cache:
+            taps, width, orig, new = resample_taps(*key)
+            cache[key] = (taps.to(self.device), width, orig, new)
+        taps, width, orig, new = cache[key]
+        rows, n, ch = x.shape
+        n_out = -(-n * new // orig)
+        y = torch.empty(rows, n_out, ch, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.resep_resample_fir(self.handle, x.data_ptr(), rows, n, y.data_ptr(), n_out, ch, orig, new, taps.data_ptr(),
+                                             taps.shape[1], width, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(self.lib, self.handle, rc)
+        return y
+
     def peak_normalize(self, est_flat: torch.Tensor, offs: list[int], lens: list[int]) -> torch.Tensor:
         """In place: every (item, speaker) source of est_flat divided by its max |.| + 1e-8 (api.py:1082).
         Returns the maxima, [B, n_spk] on the device."""
@@ -144,6 +162,25 @@ class _Engine:
             self.close()
         except Exception:
             pass
+
+
+def resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Windowed-sinc polyphase taps exactly as torchaudio.functional.resample (method "sinc_interp_hann") defines them:
+    returns (taps [new, 2 * width + orig] float32 on the CPU, width, orig, new) with orig / new reduced by their gcd."""
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1)[:, None, None] / new + idx      # (int64 / int -> float32, as torchaudio computes it)
+    t *= base
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    kernels = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t)
+    kernels *= window * (base / orig)
+    return kernels.to(torch.float32).reshape(new, -1).contiguous(), width, orig, new
 
 
 def _needs_zero_fill(offs, lens, total) -> bool:
@@ -315,11 +352,24 @@ class SepformerSeparation:
                                "Kernel size can't be greater than actual input size")
 
     @torch.no_grad()
-    def separate_batch(self, mix: torch.Tensor, peak_normalize: bool = False) -> torch.Tensor:
+    def separate_batch(self, mix: torch.Tensor, peak_normalize: bool = False, sample_rate: int | None = None) -> torch.Tensor:
         """mix [B,T] float32 (any device) -> est_sources [B,T,n_spk] float32 on ``self.device``.
         ``peak_normalize=True`` additionally applies the caller's `source / (source.abs().max() + 1e-8)`
-        (api.py:1082) to every (item, speaker) source on the device."""
+        (api.py:1082) to every (item, speaker) source on the device.
+        ``sample_rate`` (default: the model's 8000, i.e. no resampling -- what api.py does with its 16 kHz audio):
+        the rate of ``mix``; if it differs, mix is resampled to 8 kHz, separated, and the sources are resampled back,
+        all on the device, so the result is still [B,T,n_spk] at the caller's rate."""
         self._check_mix(mix)
+        if sample_rate is not None and int(sample_rate) != SAMPLE_RATE:
+            B, T = mix.shape
+            x = self._engine.resample(mix.to(self.device).contiguous().view(B, T, 1), int(sample_rate), SAMPLE_RATE)
+            est = self.separate_batch(x.view(B, -1))
+            est = self._engine.resample(est, SAMPLE_RATE, int(sample_rate))[:, :T].contiguous()
+            if est.size(1) < T:
+                est = torch.nn.functional.pad(est, (0, 0, 0, T - est.size(1)))
+            if peak_normalize:
+                self._engine.peak_normalize(est.view(-1), [b * T for b in range(B)], [T] * B)
+            return est
         B, T = mix.shape
         mix = mix.to(self.device).contiguous()
         offs, lens = [b * T for b in range(B)], [T] * B
@@ -432,7 +482,7 @@ class SepformerSeparation:
         batch, fs = torchaudio.load(path)
         batch = batch.mean(dim=0, keepdim=True).to(self.device)
         if fs != SAMPLE_RATE:
-            batch = torchaudio.functional.resample(batch, fs, SAMPLE_RATE)
+            batch = self._engine.resample(batch.float().contiguous()[:, :, None], fs, SAMPLE_RATE)[:, :, 0]
         est = self.separate_batch(batch.float())
         return est / est.abs().max(dim=1, keepdim=True)[0]
 

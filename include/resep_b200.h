@@ -133,6 +133,15 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                   float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                   void* stream);
 
+/* Polyphase FIR resampling on the device, for running the 8 kHz separator on the product's 16 kHz audio
+ * (api.py:115 feeds 16 kHz to a model whose sample_rate is 8000).  Same arithmetic as
+ * torchaudio.functional.resample: x zero-padded by `width` on the left,
+ *   y[row][m*up + p][c] = sum_j taps[p*ktaps + j] * xpad[row][m*down + j][c]
+ *   x  DEVICE fp32 [rows][n_in][channels]    y  DEVICE fp32 [rows][n_out][channels]
+ *   taps DEVICE fp32 [up][ktaps] (clearconverse_b200.separation.resample_taps builds torchaudio's windowed sinc) */
+int resep_resample_fir(ResepHandle* h, const float* x, int rows, int64_t n_in, float* y, int64_t n_out, int channels,
+                       int down, int up, const float* taps, int ktaps, int width, void* stream);
+
 /* Replaces the caller's first step on every separated source, api.py:1082
  * `source / (source.abs().max() + 1e-8)`, on the device and for all items at once:
  *   est[item][t][spk] /= max_t |est[item][t][spk]| + 1e-8   in place, layout as resep_forward's est

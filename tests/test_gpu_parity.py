@@ -429,3 +429,31 @@ def test_separate_regions_dedupes_and_matches_per_region_calls(make_sep):
         want = sep.separate_batch(audio[a:b][None])[0]
         assert o.shape == (b - a, 2)
         assert (o - want).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("orig,new,ch", [(16000, 8000, 1), (8000, 16000, 2), (44100, 8000, 1), (8000, 48000, 2)])
+def test_device_resampler_matches_torchaudio(make_sep, orig, new, ch):
+    """SURVEY 8f-2: the FIR pass against torchaudio.functional.resample on the CPU (same taps, same zero padding;
+    only the fp32 summation order differs), interleaved channels and odd lengths included."""
+    import torchaudio.functional as AF
+    sep = make_sep("fp32", "coupled")
+    g = torch.Generator().manual_seed(orig + new)
+    x = torch.randn(3, 4001, ch, generator=g)
+    got = sep._engine.resample(x.cuda(), orig, new).cpu()
+    want = AF.resample(x.permute(0, 2, 1).contiguous(), orig, new).permute(0, 2, 1)
+    assert got.shape == want.shape
+    tol = 2e-6 if max(orig, new) // min(orig, new) * min(orig, new) == max(orig, new) and max(orig, new) <= 16000 else 2e-5   # 509-tap sums for 44.1 kHz
+    assert (got - want).abs().max().item() <= tol
+
+
+def test_separate_batch_at_16k_runs_the_model_at_8k(make_sep):
+    """sample_rate=16000: resample down, separate, resample up, all on the device == the same three steps done with
+    torchaudio around a plain 8 kHz call."""
+    import torchaudio.functional as AF
+    sep = make_sep("fp32", "coupled")
+    mix16 = AF.resample(synth_batch(2, 12000, 7), 8000, 16000)[:, :23999]      # odd length on purpose
+    got = sep.separate_batch(mix16, sample_rate=16000)
+    assert got.shape == (2, 23999, 2)
+    est8 = sep.separate_batch(AF.resample(mix16, 16000, 8000)).cpu()
+    want = AF.resample(est8.permute(0, 2, 1).contiguous(), 8000, 16000).permute(0, 2, 1)[:, :23999]
+    assert (got.cpu() - want).abs().max().item() <= 1e-5
