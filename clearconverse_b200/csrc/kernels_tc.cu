@@ -425,6 +425,27 @@ constexpr int AS_ROW = 24;   // halves per staged K / V row (16 used)
 // per CTA; longer sequences take `q_tiles` CTAs).  <160, 5, 2> is the per-chunk kernel; <448, 4, 1> covers the coupled
 // memory transformer's single sequence of all chunk summaries (432 rows at config 2) with 7 x 8 CTAs instead of the
 // 3 x 8 of the streaming kernel below, which is latency-bound at that size.
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Squared norms for the softmax stabiliser, accumulated in packed bf16 (HFMA2.BF16: two elements per instruction, no
+// conversions).  Only an upper bound is needed downstream; the roundings are covered by the 1.02 margin there.
+__device__ __forceinline__ float sqnorm16_bf16(const uint32_t (&w)[8]) {
+  __nv_bfloat162 acc = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    acc = __hfma2(v, v, acc);
+  }
+  const float2 f = __bfloat1622float2(acc);
+  return f.x + f.y;
+}
+__device__ __forceinline__ float sqnorm4_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&a), vb = *reinterpret_cast<const __nv_bfloat162*>(&b);
+  const float2 f = __bfloat1622float2(__hfma2(vb, vb, __hmul2(va, va)));
+  return f.x + f.y;
+}
+
 template <int KMAX, int WARPS, int MT>
 __global__ void __launch_bounds__(32 * WARPS, KMAX <= 160 ? 6 : 2)
 k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int seq_len, const int* __restrict__ seq_off,
@@ -482,14 +503,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       kd[0] = k0; kd[1] = k1;
       vd[0] = v0; vd[1] = v1;
       const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-      float kn2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
-        kn2 = fmaf(f.x, f.x, kn2);
-        kn2 = fmaf(f.y, f.y, kn2);
-      }
-      kn2max = fmaxf(kn2max, kn2);
+      kn2max = fmaxf(kn2max, sqnorm16_bf16(kw));     // (same arithmetic as k_attention_bf16_tma: the two kernels must agree bit for bit)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kn2max = fmaxf(kn2max, __shfl_xor_sync(0xffffffffu, kn2max, o));
@@ -516,16 +530,13 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
     // violate that (never seen with LayerNorm'ed inputs) takes the exact row-maximum pass instead.
     float qn0, qn1;
     {
-      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[0]));
-      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[1]));
-      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[2]));
-      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[3]));
-      qn0 = a0.x * a0.x + a0.y * a0.y + a2.x * a2.x + a2.y * a2.y;     // row g:     dims 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
-      qn1 = a1.x * a1.x + a1.y * a1.y + a3.x * a3.x + a3.y * a3.y;     // row g + 8
+      qn0 = sqnorm4_bf16(qa[0], qa[2]);               // row g:     dims 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
+      qn1 = sqnorm4_bf16(qa[1], qa[3]);               // row g + 8
       qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
-    float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;   // upper bounds of the raw scores
+    // upper bounds of the raw scores; margin: the packed-bf16 squared norms may each come out up to 1.6 % low
+    float mx0 = sqrt_approx(qn0 * kmax2) * 1.02f, mx1 = sqrt_approx(qn1 * kmax2) * 1.02f;
     float mb = fmaxf(mx0, mx1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
@@ -592,7 +603,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
 #pragma unroll 3
     for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
     pv_block(nkk - 1, std::true_type{});
-    const float i0 = 1.f / ol[0], i1 = 1.f / ol[2];
+    const float i0 = rcp_approx(ol[0]), i1 = rcp_approx(ol[2]);
     const int r0 = row0 + g, r1 = row0 + g + 8;
     if (r0 < len) {
       bf16* op = ctx + (int64_t)(off + r0) * D + head * DH + 2 * t4;
@@ -617,8 +628,6 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
 // (+ 32 B of the next head, unused; zero-filled past column 384), 128B-swizzled so ldmatrix reads it conflict-free.
 // Rows past the sequence inside a box belong to the next chunk: as keys they are masked (last block), as queries
 // they are computed and never stored; past the end of the tensor TMA fills zeros.
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
 __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx,
                                                                 int seq_len) {
   __shared__ __align__(1024) bf16 Ts[160 * 64];      // row r: 16-byte chunk c at c ^ (r & 7); chunks 0,1 = q, 2,3 = k, 4,5 = v
@@ -646,13 +655,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     const uint4 ka = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((2 ^ r7) << 3));
     const uint4 kb = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((3 ^ r7) << 3));
     const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-    float kn2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[i]));
-      kn2 = fmaf(f.x, f.x, kn2);
-      kn2 = fmaf(f.y, f.y, kn2);
-    }
+    float kn2 = sqnorm16_bf16(kw);
     if ((int)threadIdx.x >= len) kn2 = 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
@@ -677,16 +680,13 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     // softmax stabiliser from the Cauchy-Schwarz bound (see k_attention_bf16_short); exact row maxima as fallback
     float qn0, qn1;
     {
-      const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[0]));
-      const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[1]));
-      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[2]));
-      const float2 a3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qa[3]));
-      qn0 = a0.x * a0.x + a0.y * a0.y + a2.x * a2.x + a2.y * a2.y;
-      qn1 = a1.x * a1.x + a1.y * a1.y + a3.x * a3.x + a3.y * a3.y;
+      qn0 = sqnorm4_bf16(qa[0], qa[2]);               // row g:     a0 (k 0-1 of this lane's quad), a2 (k 8-9)
+      qn1 = sqnorm4_bf16(qa[1], qa[3]);               // row g + 8: a1, a3
       qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
-    float mx0 = sqrt_approx(qn0 * kmax2) * 1.0001f, mx1 = sqrt_approx(qn1 * kmax2) * 1.0001f;   // (2 ulp of MUFU.SQRT << the margin)
+    // margin: the packed-bf16 squared norms may each come out up to 1.6 % low (8 roundings of 2^-9), MUFU.SQRT 2 ulp
+    float mx0 = sqrt_approx(qn0 * kmax2) * 1.02f, mx1 = sqrt_approx(qn1 * kmax2) * 1.02f;
     const bool big = !((row0 + g < len ? mx0 : 0.f) * (0.5f / QK_PRESCALE) < 80.f) || !((row0 + g + 8 < len ? mx1 : 0.f) * (0.5f / QK_PRESCALE) < 80.f);   // query rows past the sequence do not vote
     if (__any_sync(0xffffffffu, big)) {                         // warp-uniform; also taken for NaN / inf inputs
       mx0 = -INFINITY; mx1 = -INFINITY;
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
 #pragma unroll 3
     for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
     pv_block(nkk - 1, std::true_type{});
-    const float i0 = 1.f / ol[0], i1 = 1.f / ol[2];
+    const float i0 = rcp_approx(ol[0]), i1 = rcp_approx(ol[2]);   // 1 ulp; the result is rounded to bf16 next
     const int r0 = row0 + g, r1 = row0 + g + 8;
     if (r0 < len) {
       bf16* op = ctx + (off + r0) * D + head * DH + 2 * t4;
