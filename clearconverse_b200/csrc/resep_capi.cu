@@ -544,6 +544,10 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
   if (!h) return set_err(nullptr, RESEP_EINVAL, "out of host memory");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* r = getenv("RESEP_RESERVE_SMS")) {   // persistent kernels leave this many SMs to a concurrent forward's small kernels
+    const int k = atoi(r);
+    if (k > 0 && k < h->sm_count - 2) h->sm_count -= k;
+  }
   if (const char* m = getenv("RESEP_W16")) {   // weight operand of the bf16 mode (see DESIGN.md "precision modes")
     if (!strcmp(m, "bf16")) h->w16_mode = 0;          // single rounded bf16 weight: fails the SI-SNR gate
     else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;   // every weight as hi + lo

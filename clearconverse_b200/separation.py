@@ -52,7 +52,7 @@ class _Engine:
         cfg = _weights.default_config()
         rc = self.lib.resep_create(C.byref(cfg), C.byref(self.packed.struct), self.device.index, C.byref(self.handle))
         _lib.check(self.lib, None, rc)
-        self.workspace = None
+        self.workspaces: dict = {}        # lane -> tensor (a lane = one CUDA stream's worth of in-flight forwards)
         self._static_io: dict = {}        # (offs, lens, slot) -> (mix_buf, est_buf): fixed addresses let the C side replay a CUDA graph
         with _ENGINES_LOCK:
             self.id = _NEXT_ID[0]
@@ -67,13 +67,15 @@ class _Engine:
     def launch_count(self) -> int:
         return int(self.lib.resep_launch_count(self.handle))
 
-    def _workspace_for(self, lens: "C.Array", B: int, precision: int) -> torch.Tensor:
+    def _workspace_for(self, lens: "C.Array", B: int, precision: int, lane: int = 0) -> torch.Tensor:
         need = C.c_size_t()
         _lib.check(self.lib, self.handle, self.lib.resep_workspace_bytes(self.handle, B, lens, precision, C.byref(need)))
-        if self.workspace is None or self.workspace.numel() < need.value:
-            self.workspace = None          # release before growing
-            self.workspace = torch.empty(int(need.value * 1.0) + 1024, dtype=torch.uint8, device=self.device)
-        return self.workspace
+        ws = self.workspaces.get(lane)
+        if ws is None or ws.numel() < need.value:
+            self.workspaces.pop(lane, None)          # release before growing
+            ws = torch.empty(int(need.value * 1.0) + 1024, dtype=torch.uint8, device=self.device)
+            self.workspaces[lane] = ws
+        return ws
 
     def static_io(self, offs, lens, total: int, slot: int = 0):
         """Persistent (mix, est) device buffers for one batch shape.  The C ABI keys its CUDA graphs on buffer
@@ -90,14 +92,15 @@ class _Engine:
         return io
 
     def forward(self, mix_flat: torch.Tensor, offs: list[int], lens: list[int], precision: int, batch_mode: int,
-                debug: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                debug: dict | None = None, out: torch.Tensor | None = None, lane: int = 0) -> torch.Tensor:
         """mix_flat: 1-D fp32 CUDA tensor holding every item; returns est_flat [2 * mix_flat.numel()]
-        (``out`` if given: it must be zero-filled where items leave gaps)."""
+        (``out`` if given: it must be zero-filled where items leave gaps).  Forwards that may be in flight at the same
+        time (different CUDA streams) must use different ``lane``s: a lane owns a workspace."""
         B = len(lens)
         c_off = (C.c_int64 * B)(*offs)
         c_len = (C.c_int64 * B)(*lens)
         with torch.cuda.device(self.device):
-            ws = self._workspace_for(c_len, B, precision)
+            ws = self._workspace_for(c_len, B, precision, lane)
             if out is not None:
                 est = out
             else:
@@ -216,7 +219,7 @@ def _resep_separate_static(host_or_dev_mix: torch.Tensor, offs: list[int], lens:
     if eng is None:
         raise RuntimeError("clearconverse_b200: separator engine was destroyed")
     _, est_buf = eng.static_io(offs, lens, host_or_dev_mix.numel(), slot)
-    eng.forward(host_or_dev_mix, offs, lens, precision, batch_mode, out=est_buf)
+    eng.forward(host_or_dev_mix, offs, lens, precision, batch_mode, out=est_buf, lane=slot & 1)
     return est_buf
 
 
@@ -420,15 +423,21 @@ class SepformerSeparation:
         return [outs[i] for i in inverse]
 
     @torch.no_grad()
-    def separate_stream(self, batches, out_buffers=None, depth: int = 2):
+    def separate_stream(self, batches, out_buffers=None, depth: int = 2, device_out: bool = False):
         """Pipelined driver for a sequence of HOST batches (the batched overlap driver of SURVEY.md section 8f-1):
         yields, in order, a pinned HOST tensor [B,T,n_spk] per input batch.  The host->device copy of batch i+1 and
         the device->host copy of batch i-1 run on their own streams under the kernels of batch i, so the copies cost
         no throughput.  ``batches``: iterable of [B,T] float32 CPU tensors (pinned for truly asynchronous copies);
         ``out_buffers``: optional list of >= ``depth`` pinned [B,T,n_spk] tensors to reuse (a yielded tensor is
-        overwritten ``depth`` batches later)."""
+        overwritten ``depth`` batches later).  Batches that already live on the device are taken as they are (no host
+        copy); ``device_out=True`` yields device tensors (new ones, owned by the caller) instead of host tensors."""
         dev = self.device
-        compute = torch.cuda.current_stream(dev)
+        # Two compute streams, batches alternating between them (each lane has its own workspace and CUDA graphs): a
+        # forward spends ~12 % of its time in the memory transformer, whose 24 latency-bound launches use 4-56 CTAs;
+        # the neighbouring batch's intra block fills those SMs (scripts/gpu_timeline.py, scripts/gpu_dual_stream.py).
+        lanes = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if depth >= 2 else [torch.cuda.current_stream(dev)]
+        for st in lanes:
+            st.wait_stream(torch.cuda.current_stream(dev))
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         inflight = []                                     # (event, host_out)
 
@@ -441,15 +450,29 @@ class SepformerSeparation:
             self._check_mix(mix)
             B, T = mix.shape
             offs, lens, slot = [b * T for b in range(B)], [T] * B, i % depth
+            compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
             # slot i % depth was last used by batch i - depth, whose result has been drained (synchronised) already
             mix_buf, _ = self._engine.static_io(offs, lens, B * T, slot)
-            with torch.cuda.stream(h2d):
-                mix_buf.copy_(mix.reshape(-1), non_blocking=True)
-                up = torch.cuda.Event(); up.record(h2d)
-            compute.wait_event(up)
-            est = torch.ops.clearconverse_b200.resep_separate_static(
-                mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision],
-                _lib.BATCH_MODES[self.batch_mode], slot).view(B, T, NUM_SPKS)
+            if mix.is_cuda:
+                with torch.cuda.stream(compute):
+                    mix_buf.copy_(mix.reshape(-1), non_blocking=True)
+            else:
+                with torch.cuda.stream(h2d):
+                    mix_buf.copy_(mix.reshape(-1), non_blocking=True)
+                    up = torch.cuda.Event(); up.record(h2d)
+                compute.wait_event(up)
+            with torch.cuda.stream(compute):
+                est = torch.ops.clearconverse_b200.resep_separate_static(
+                    mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision],
+                    _lib.BATCH_MODES[self.batch_mode], slot).view(B, T, NUM_SPKS)
+            if device_out:
+                with torch.cuda.stream(compute):
+                    res = est.clone()
+                    fin = torch.cuda.Event(); fin.record(compute)
+                inflight.append((fin, res))
+                if len(inflight) >= depth:
+                    yield drain_one()
+                continue
             done = torch.cuda.Event(); done.record(compute)
             if out_buffers is not None:
                 host = out_buffers[i % len(out_buffers)]

@@ -319,6 +319,20 @@ def test_separate_stream_equals_separate_batch(sep_fp32):
         assert torch.equal(o, sep_fp32.separate_batch(b).cpu())
 
 
+def test_separate_stream_two_lanes_bf16(make_sep):
+    """bf16: batches alternate between two compute streams (own workspace and CUDA graphs per lane) so that one batch's
+    memory transformer overlaps the next batch's intra block; results must equal the one-at-a-time calls, for every
+    pipeline depth, over enough batches for the graphs of both lanes to be captured and replayed."""
+    sep = make_sep("bf16", "coupled")
+    batches = [synth_batch(3, 9000, 70 + i).pin_memory() for i in range(4)]
+    want = [sep.separate_batch(b).cpu() for b in batches]
+    for depth in (1, 2, 3):
+        outs = [o.clone() for o in sep.separate_stream((batches[i % 4] for i in range(9)), depth=depth)]
+        assert len(outs) == 9
+        for i, o in enumerate(outs):
+            assert torch.equal(o, want[i % 4]), (depth, i)
+
+
 def test_bf16_graph_replay_is_bit_identical_to_eager(make_sep):
     """The C ABI runs a forward eagerly the first time it sees a (shapes, buffers) key, captures a CUDA graph the
     second time and replays it afterwards: all three must give the same bits (the bf16 path has no atomics)."""
