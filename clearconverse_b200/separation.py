@@ -435,10 +435,12 @@ class SepformerSeparation:
         # Two compute streams, batches alternating between them (each lane has its own workspace and CUDA graphs): a
         # forward spends ~12 % of its time in the memory transformer, whose 24 latency-bound launches use 4-56 CTAs;
         # the neighbouring batch's intra block fills those SMs (scripts/gpu_timeline.py, scripts/gpu_dual_stream.py).
-        lanes = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if depth >= 2 else [torch.cuda.current_stream(dev)]
-        for st in lanes:
+        if getattr(self, "_pipe_streams", None) is None:   # created once: the caching allocator keeps per-stream pools,
+            self._pipe_streams = [torch.cuda.Stream(dev) for _ in range(4)]   # fresh streams mean fresh cudaMallocs
+        lanes = self._pipe_streams[:2] if depth >= 2 else [torch.cuda.current_stream(dev)]
+        h2d, d2h = self._pipe_streams[2], self._pipe_streams[3]
+        for st in self._pipe_streams:
             st.wait_stream(torch.cuda.current_stream(dev))
-        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         inflight = []                                     # (event, host_out)
 
         def drain_one():
