@@ -7,9 +7,9 @@ import torch
 from clearconverse_b200 import SepformerSeparation, synth, weights
 sds = weights.random_init_state_dicts(0)
 K = 40
-seps = [SepformerSeparation(sds, device="cuda:0", precision="bf16") for _ in range(2)]
-mixes = [synth.synth_batch(16, 32000, 1 + i).cuda() for i in range(2)]
-streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+seps = [SepformerSeparation(sds, device="cuda:0", precision="bf16") for _ in range(3)]
+mixes = [synth.synth_batch(16, 32000, 1 + i).cuda() for i in range(3)]
+streams = [torch.cuda.Stream() for _ in range(3)]
 def run(n_streams):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -19,6 +19,6 @@ def run(n_streams):
             seps[j].separate_batch(mixes[j])
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / K * 1e3
-for n in (1, 2):
+for n in (1, 2, 3):
     for _ in range(2): run(n)
     print(f"{n} stream(s): {run(n):.4f} ms per forward, {16*4/run(n)*1e3:.0f} audio-s/s")
