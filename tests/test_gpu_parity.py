@@ -43,7 +43,7 @@ def si_snr_delta(est: torch.Tensor, oracle_est: torch.Tensor, mix: torch.Tensor,
     max over (item, speaker) of |SI-SNR(est, mix) - SI-SNR(oracle_est, mix)| in dB, over the pairs whose oracle
     SI-SNR is >= min_ref_db.  A perturbation S dB below the estimate can move an SI-SNR of R dB by up to
     20 log10(1 + 10^((|R| - S) / 20)): for R -> -inf (estimate orthogonal to the reference) any perturbation
-    moves it arbitrarily.  Measured with four weight seeds (scripts/gpu_fc_probe.py): S = 49.8 ... 52.9 dB
+    moves it arbitrarily.  Measured with four weight seeds (scripts/gpu_accuracy.py): S = 49.8 ... 52.9 dB
     everywhere; delta <= 0.043 dB for R >= -22 dB, 0.05-0.08 around -25 ... -31 dB, 0.15-1.3 dB below -45 dB.  A
     trained separator sits at R >> 0 dB.  The pairs left out here are still held to MIN_EST_VS_EST_DB."""
     a = si_snr_db(est.permute(0, 2, 1), mix[:, None, :])
@@ -103,6 +103,23 @@ def test_fp32_forward_matches_oracle(sep_fp32, oracle, B, T, seed):
     got = sep_fp32.separate_batch(mix)
     assert got.shape == (B, T, 2) and got.dtype == torch.float32 and got.is_cuda and got.is_contiguous()
     assert (got.cpu() - want).abs().max().item() < TOL_FP32
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16_MAXABS)])
+def test_frame_and_chunk_boundaries(make_sep, oracle, prec, tol):
+    """Lengths around every boundary of the path: T % 8 (trailing zeros), L % 150 (1,200 / 2,400 samples: L = 149 / 299,
+    no spare token row in the bf16 fused tail; 1,208 / 2,408: L = 150 / 300 -> an extra all-zero chunk), single frames.
+    One ragged independent batch against per-item oracle calls."""
+    sep = make_sep(prec, "independent")
+    lens = [16, 17, 23, 24, 1199, 1200, 1207, 1208, 1215, 1216, 2400, 2407, 2408]
+    segs = [synth_mixture(n, 300 + i)[0] for i, n in enumerate(lens)]
+    outs = sep.separate_segments(segs)
+    for n, s_, o in zip(lens, segs, outs):
+        want = oracle.separate_batch(s_[None])[0]
+        assert o.shape == want.shape == (n, 2)
+        assert (o.cpu() - want).abs().max().item() <= tol, n
+        t_est = 8 * ((n - 16) // 8) + 16
+        assert torch.count_nonzero(o[t_est:]).item() == 0, n          # upstream's F.pad: exact zeros past T_est
 
 
 def test_intermediates_match_functional_restatement(sep_fp32, sds):
@@ -394,7 +411,8 @@ def test_fused_mask_decoder_matches_unfused(sds, cuda_lib_built):
         "from clearconverse_b200 import SepformerSeparation, synth, weights\n"
         "sep = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision='bf16', batch_mode='independent')\n"
         "outs = {}\n"
-        "for name, lens in (('ragged', [32000, 16, 1211, 4000, 9000, 1208, 23, 8191]), ('fallback', [1203, 4000]), ('one', [2000])):\n"
+        "for name, lens in (('ragged', [32000, 16, 1211, 4000, 9000, 1208, 23, 8191]), ('fallback', [1203, 4000]), ('one', [2000]),\n"
+        "                   ('edges', [1200, 1199, 1207, 1208, 1215, 1216, 2400, 2407, 2408, 17, 24]), ('exact', [1200]), ('exact2', [2400, 1200])):\n"
         "    segs = [synth.synth_mixture(n, 40 + i)[0] for i, n in enumerate(lens)]\n"
         "    outs[name] = [o.cpu() for o in sep.separate_segments(segs)]\n"
         "sepc = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision='bf16', batch_mode='coupled')\n"
