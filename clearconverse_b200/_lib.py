@@ -42,6 +42,10 @@ class ResepWeights(C.Structure):
                 ("pe_rows", C.c_int64), ("seg", ResepBlockWeights * 2), ("mem", ResepBlockWeights * 1)]
 
 
+class ResepSpanCtl(C.Structure):
+    _fields_ = [("phase", C.c_int), ("inner", C.c_int), ("chunk_means", C.c_void_p), ("hc", C.c_void_p)]
+
+
 class ResepDebugOut(C.Structure):
     _fields_ = [(n, _fp) for n in ("enc", "seg0", "chunk_mean", "mem0", "seg1")]
 
@@ -57,6 +61,9 @@ SYMBOLS = {
     "resep_workspace_bytes": (C.c_int, [_H, C.c_int, _i64p, C.c_int, C.POINTER(C.c_size_t)]),
     "resep_forward": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                 C.c_int, C.c_int, C.c_void_p]),
+    "resep_forward_span": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "resep_memory_workspace_bytes": (C.c_int, [_H, C.c_int, C.POINTER(C.c_size_t)]),
+    "resep_memory_block": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "resep_resample_fir": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_int, C.c_int, C.c_void_p]),
     "resep_peak_normalize": (C.c_int, [_H, C.c_void_p, _i64p, _i64p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -199,6 +199,7 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
     if (L > 2000000000LL / D) { delete p; return set_err(h, RESEP_EINVAL, "item too long"); }
     item_L[i] = (int)L;
     item_S[i] = (int)(L / CHUNK + 1);   // rest = K - L % K is in [1, K]: a full zero chunk when L % K == 0
+    if (batch_mode == RESEP_BATCH_SPAN_EXACT && L % CHUNK == 0) item_S[i] = (int)(L / CHUNK);   // inner span of a longer recording
     item_row0[i] = (int)(chunks * CHUNK);
     chunks += item_S[i];
     if (chunks * CHUNK > 2000000000LL) { delete p; return set_err(h, RESEP_EINVAL, "batch too large (token rows overflow int32)"); }
@@ -367,7 +368,7 @@ static int run_block(ResepHandle* h, int blk, const float* xprev, const float* h
 
 static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
                          float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
-                         cudaStream_t st, const ResepDebugOut* dbg);
+                         cudaStream_t st, const ResepDebugOut* dbg, const ResepSpanCtl* span = nullptr);
 
 static void drop_graphs(ResepHandle* h) {
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -440,12 +441,14 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
 
 static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_off, const int64_t* item_len, int B,
                          float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
-                         cudaStream_t st, const ResepDebugOut* dbg) {
+                         cudaStream_t st, const ResepDebugOut* dbg, const ResepSpanCtl* span) {
   if (!h) return RESEP_EINVAL;
   if (!mix || !item_off || !item_len || !est || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or B <= 0");
   if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
-  if (batch_mode != RESEP_BATCH_COUPLED && batch_mode != RESEP_BATCH_INDEPENDENT)
+  if (batch_mode != RESEP_BATCH_COUPLED && batch_mode != RESEP_BATCH_INDEPENDENT && !(span && batch_mode == RESEP_BATCH_SPAN_EXACT))
     return set_err(h, RESEP_EINVAL, "unknown batch_mode");
+  // span != nullptr: one phase of a forward whose memory transformer runs elsewhere (resep_forward_span)
+  const bool phase1 = span && span->phase == 1, phase2 = span && span->phase == 2;
   RESEP_CUDA(h, cudaSetDevice(h->device));
   Plan* p = nullptr;
   int rc = get_plan(h, B, item_off, item_len, batch_mode, st, &p);
@@ -455,7 +458,7 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
   if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
 
-  if ((rc = launch_encoder_chunked(h, mix, *p, ws.x0, st))) return rc;
+  if (!phase2 && (rc = launch_encoder_chunked(h, mix, *p, ws.x0, st))) return rc;
   if (dbg && dbg->enc) RESEP_CUDA(h, cudaMemcpyAsync(dbg->enc, ws.x0, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   SeqDesc intra{p->M, (int)p->n_chunks, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK};
@@ -483,12 +486,18 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     return RESEP_OK;
   };
   // seg_model[0](x + 0): skip input is the encoder output itself
-  if ((rc = run_intra(0, ws.x0, nullptr, ws.x0, ws.a, ws.hc_in, nullptr))) return rc;
+  if (!phase2 && (rc = run_intra(0, ws.x0, nullptr, ws.x0, ws.a, ws.hc_in, nullptr))) return rc;
+  if (phase1) {
+    RESEP_CUDA(h, cudaMemcpyAsync(span->chunk_means, ws.hc_in, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return RESEP_OK;
+  }
   if (dbg && dbg->seg0) RESEP_CUDA(h, cudaMemcpyAsync(dbg->seg0, ws.a, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (dbg && dbg->chunk_mean)
     RESEP_CUDA(h, cudaMemcpyAsync(dbg->chunk_mean, ws.hc_in, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // mem_model[0](chunk means): memory transformer over chunk summaries
-  if ((rc = run_block(h, 2, ws.hc_in, nullptr, ws.hc_in, ws.o, ws.hc_out, nullptr, mem, ws, precision, st))) return rc;
+  if (phase2)
+    RESEP_CUDA(h, cudaMemcpyAsync(ws.hc_out, span->hc, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else if ((rc = run_block(h, 2, ws.hc_in, nullptr, ws.hc_in, ws.o, ws.hc_out, nullptr, mem, ws, precision, st))) return rc;
   if (dbg && dbg->mem0)
     RESEP_CUDA(h, cudaMemcpyAsync(dbg->mem0, ws.hc_out, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // seg_model[1](out + hc)
@@ -656,6 +665,43 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                   void* workspace, size_t workspace_bytes, int precision, int batch_mode, void* stream) {
   return forward_impl(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode,
                       static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int resep_forward_span(ResepHandle* h, const float* mix, int64_t span_len, float* est, void* workspace, size_t workspace_bytes,
+                       int precision, void* stream, const ResepSpanCtl* ctl) {
+  if (!h) return RESEP_EINVAL;
+  if (!ctl || (ctl->phase != 1 && ctl->phase != 2) || (ctl->phase == 1 && !ctl->chunk_means) || (ctl->phase == 2 && !ctl->hc))
+    return set_err(h, RESEP_EINVAL, "forward_span: bad control block");
+  const int64_t off = 0;
+  return forward_eager(h, mix, &off, &span_len, 1, est, workspace, workspace_bytes, precision,
+                       ctl->inner ? RESEP_BATCH_SPAN_EXACT : RESEP_BATCH_INDEPENDENT, static_cast<cudaStream_t>(stream), nullptr, ctl);
+}
+
+int resep_memory_workspace_bytes(ResepHandle* h, int n_chunks, size_t* bytes) {
+  if (!h) return RESEP_EINVAL;
+  if (!bytes || n_chunks <= 0) return set_err(h, RESEP_EINVAL, "null pointer or n_chunks <= 0");
+  *bytes = carve(nullptr, n_chunks, n_chunks).bytes;
+  return RESEP_OK;
+}
+
+int resep_memory_block(ResepHandle* h, const float* chunk_means, float* hc, int n_chunks, void* workspace, size_t workspace_bytes,
+                       int precision, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!chunk_means || !hc || n_chunks <= 0) return set_err(h, RESEP_EINVAL, "null pointer or n_chunks <= 0");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  if (n_chunks > h->w.pe_rows) return set_err(h, RESEP_EPOS, "memory sequence longer than the positional-encoding table");
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace ws = carve(workspace, n_chunks, n_chunks);
+  if (!workspace || workspace_bytes < ws.bytes)
+    return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
+  int rc;
+  if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
+  RESEP_CUDA(h, cudaMemcpyAsync(ws.hc_in, chunk_means, (size_t)n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SeqDesc mem{n_chunks, 1, n_chunks, nullptr, nullptr, nullptr, nullptr, 0, n_chunks};
+  if ((rc = run_block(h, 2, ws.hc_in, nullptr, ws.hc_in, ws.o, ws.hc_out, nullptr, mem, ws, precision, st))) return rc;
+  RESEP_CUDA(h, cudaMemcpyAsync(hc, ws.hc_out, (size_t)n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return RESEP_OK;
 }
 
 int resep_resample_fir(ResepHandle* h, const float* x, int rows, int64_t n_in, float* y, int64_t n_out, int channels, int down,

@@ -17,6 +17,8 @@ constexpr int D = 128;       // d_model == encoder filters
 constexpr int KSZ = 16;      // encoder / decoder kernel
 constexpr int STRIDE = 8;
 constexpr int CHUNK = 150;   // segment_size K
+// internal batch mode of resep_forward_span's inner spans: one item, no padding chunk when L % 150 == 0
+constexpr int RESEP_BATCH_SPAN_EXACT = 2;
 constexpr int NH = 8;
 constexpr int DH = 16;
 // bf16 qkv buffer: row = [head 0: q16 k16 v16 | head 1: ... ] (the fp32 / tf32 paths keep torch's [q128 | k128 | v128])

@@ -124,6 +124,51 @@ class _Engine:
             _lib.check(self.lib, self.handle, rc)
         return est
 
+    # ---- one recording split by chunks (sharding.separate_long): phases of resep_forward_span + the memory block
+    def _span_call(self, phase: int, mix_ptr: int, span_len: int, est_ptr: int, inner: bool, precision: str, lane: int,
+                   means_ptr: int = 0, hc_ptr: int = 0):
+        lens = (C.c_int64 * 1)(span_len)
+        prec = _lib.PRECISIONS[precision]
+        with torch.cuda.device(self.device):
+            ws = self._workspace_for(lens, 1, prec, ("span", lane))
+            ctl = _lib.ResepSpanCtl(phase, 1 if inner else 0, means_ptr, hc_ptr)
+            rc = self.lib.resep_forward_span(self.handle, mix_ptr, span_len, est_ptr, ws.data_ptr(), ws.numel(), prec,
+                                             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), C.byref(ctl))
+        _lib.check(self.lib, self.handle, rc)
+
+    def span_phase1(self, mix_span: torch.Tensor, inner: bool, precision: str, lane: int = 0) -> torch.Tensor:
+        """encoder + seg_model[0] on one span (device tensor [span_len]) -> chunk summaries [n_chunks, 128]."""
+        n = int(mix_span.numel())
+        L = (n - KERNEL_SIZE) // 8 + 1
+        n_chunks = L // 150 if (inner and L % 150 == 0) else L // 150 + 1
+        means = torch.empty(n_chunks, 128, dtype=torch.float32, device=self.device)
+        dummy = torch.empty(2, dtype=torch.float32, device=self.device)
+        self._span_call(1, mix_span.data_ptr(), n, dummy.data_ptr(), inner, precision, lane, means_ptr=means.data_ptr())
+        return means
+
+    def span_phase2(self, span_len: int, hc: torch.Tensor, inner: bool, precision: str, lane: int = 0) -> torch.Tensor:
+        """seg_model[1](out + hc) + mask + decoder of the span whose phase 1 ran in the same lane -> est [span_len, 2]."""
+        est = torch.zeros(span_len, NUM_SPKS, dtype=torch.float32, device=self.device)
+        dummy = torch.empty(2, dtype=torch.float32, device=self.device)
+        self._span_call(2, dummy.data_ptr(), span_len, est.data_ptr(), inner, precision, lane, hc_ptr=hc.data_ptr())
+        return est
+
+    def memory_block(self, chunk_means: torch.Tensor, precision: str) -> torch.Tensor:
+        """mem_model[0] over one sequence of chunk summaries [S, 128] -> [S, 128]."""
+        S = int(chunk_means.shape[0])
+        need = C.c_size_t()
+        _lib.check(self.lib, self.handle, self.lib.resep_memory_workspace_bytes(self.handle, S, C.byref(need)))
+        hc = torch.empty_like(chunk_means)
+        with torch.cuda.device(self.device):
+            ws = self.workspaces.get("mem")
+            if ws is None or ws.numel() < need.value:
+                ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+                self.workspaces["mem"] = ws
+            rc = self.lib.resep_memory_block(self.handle, chunk_means.contiguous().data_ptr(), hc.data_ptr(), S, ws.data_ptr(), ws.numel(),
+                                             _lib.PRECISIONS[precision], C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(self.lib, self.handle, rc)
+        return hc
+
     def resample(self, x: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
         """x [rows, n, channels] fp32 on the device -> [rows, ceil(n * new / orig), channels]; torchaudio.functional.resample's
         arithmetic (its zero padding included) as one FIR pass on the device."""

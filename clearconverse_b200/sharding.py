@@ -128,3 +128,89 @@ def separate_sharded(segments, separate_fn, rank: int = 0, world_size: int = 1, 
     for part in gathered:
         merged.update(part)
     return [merged[i] for i in range(len(segments))], samples
+
+
+# ---------------------------------------------------------------------------------------------
+# One long recording split across ranks (optional row): the intra blocks are per chunk, so
+# every rank takes a contiguous chunk range; the only data-path exchange is the chunk summaries [S, 128].
+SAMPLES_PER_CHUNK = CHUNK * 8          # 150 frames x stride 8
+
+
+def split_long(T: int, parts: int):
+    """Cut one recording of T samples into at most ``parts`` spans on chunk boundaries.
+    Returns a list of (sample_start, sample_end, first_chunk, n_chunks, inner): inner spans are [1200 c0, 1200 c1 + 8)
+    (whole chunks + the decoder's 8-sample tail, overlapping the next span by 8 samples), the last span runs to T and
+    is an ordinary item (it carries upstream's padding chunk).  Every span holds at least one real frame."""
+    L = frames_of(T)
+    real = -(-L // CHUNK)                       # chunks that hold at least one real frame
+    parts = max(1, min(parts, real))
+    base, extra = divmod(real, parts)
+    spans, c0 = [], 0
+    for r in range(parts):
+        n = base + (1 if r < extra else 0)
+        last = r == parts - 1
+        if last:
+            spans.append((c0 * SAMPLES_PER_CHUNK, T, c0, chunks_of(T) - c0, False))
+        else:
+            spans.append((c0 * SAMPLES_PER_CHUNK, (c0 + n) * SAMPLES_PER_CHUNK + 8, c0, n, True))
+        c0 += n
+    return spans
+
+
+def assemble_spans(spans, ests, T: int):
+    """Overlap-add the per-span outputs ([len_r, n_spk], any device) into [T, n_spk]: neighbouring spans overlap by the
+    8 samples where one holds the upper decoder taps of its last frame and the other the lower taps of its first."""
+    import torch
+    out = torch.zeros(T, ests[0].shape[1], dtype=ests[0].dtype, device=ests[0].device)
+    for (a, b, _, _, _), e in zip(spans, ests):
+        out[a:b] += e.to(out.device)
+    return out
+
+
+def separate_long(sep, mix, rank: int = 0, world_size: int = 1, group=None, parts: int | None = None):
+    """mix: 1-D float32 recording.  With ``group`` (torch.distributed, one rank per GPU) every rank runs its span and
+    the summaries / results are exchanged with all_gather; without a group the ``parts`` (default: world_size) spans
+    run one after the other on this separator's device -- the same arithmetic, and a way to bound the workspace of a
+    recording that is too long for one launch sequence.  Returns est [T, n_spk] on ``sep.device`` (every rank)."""
+    import torch
+    eng = sep._engine
+    mix = mix.reshape(-1)
+    T = int(mix.numel())
+    spans = split_long(T, parts if parts is not None else world_size)
+    n_parts = len(spans)
+    S = spans[-1][2] + spans[-1][3]
+    dev = sep.device
+    local = list(range(n_parts)) if group is None else ([rank] if rank < n_parts else [])
+    means = {}
+    for r in local:                                   # phase 1: encoder + seg_model[0] -> chunk summaries
+        a, b, c0, n, inner = spans[r]
+        means[r] = eng.span_phase1(mix[a:b].to(dev).contiguous(), inner, sep.precision, lane=r)
+    all_means = torch.zeros(S, 128, dtype=torch.float32, device=dev)
+    if group is None:
+        for r in local:
+            all_means[spans[r][2]:spans[r][2] + spans[r][3]] = means[r]
+    else:
+        import torch.distributed as dist
+        nmax = max(sp[3] for sp in spans)
+        mine = torch.zeros(nmax, 128, dtype=torch.float32, device=dev)
+        if local:
+            mine[:spans[rank][3]] = means[rank]
+        gathered = [torch.empty_like(mine) for _ in range(world_size)]
+        dist.all_gather(gathered, mine, group=group)  # THE exchange of this path: S x 128 fp32 in total
+        for r in range(n_parts):
+            all_means[spans[r][2]:spans[r][2] + spans[r][3]] = gathered[r][:spans[r][3]]
+    hc = eng.memory_block(all_means, sep.precision)   # every rank, redundantly (its gLN needs the whole sequence anyway)
+    ests = {}
+    for r in local:                                   # phase 2: seg_model[1] + mask + decoder
+        a, b, c0, n, inner = spans[r]
+        ests[r] = eng.span_phase2(b - a, hc[c0:c0 + n].contiguous(), inner, sep.precision, lane=r)
+    if group is None:
+        return assemble_spans(spans, [ests[r] for r in range(n_parts)], T)
+    import torch.distributed as dist
+    lmax = max(sp[1] - sp[0] for sp in spans)
+    mine = torch.zeros(lmax, 2, dtype=torch.float32, device=dev)
+    if local:
+        mine[:ests[rank].shape[0]] = ests[rank]
+    gathered = [torch.empty_like(mine) for _ in range(world_size)]
+    dist.all_gather(gathered, mine, group=group)
+    return assemble_spans(spans, [gathered[r][:spans[r][1] - spans[r][0]] for r in range(n_parts)], T)

@@ -133,6 +133,29 @@ int resep_forward(ResepHandle* h, const float* mix, const int64_t* item_off, con
                   float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                   void* stream);
 
+/* One long recording split by chunks across several GPUs (optional row): the intra blocks are per chunk,
+ * so rank r runs them on its contiguous chunk range; the only exchange is the chunk summaries.
+ *   phase 1  encoder + seg_model[0] on the span            -> chunk_means [n,128]   (all-gather these, in span order)
+ *   resep_memory_block on the FULL sequence of summaries    -> hc [S,128]           (every rank, redundantly)
+ *   phase 2  seg_model[1](out + hc rows of the span) + mask + decoder -> est [span_len, 2]
+ * A span that ends inside the recording (`inner` = 1) must hold a whole number of chunks plus the decoder's 8-sample
+ * tail: span_len = 1200 * n + 8; it gets no padding chunk, and its last 8 output samples are the upper filter taps of
+ * its last frame, to be ADDED to the first 8 samples of the next span's output (overlap-add across the cut).  The last
+ * span (`inner` = 0) is an ordinary item.  Both phases must be given the same workspace (resep_workspace_bytes for one
+ * item of span_len samples); results are bit-identical to the unsplit resep_forward. */
+typedef struct ResepSpanCtl {
+  int phase;              /* 1 or 2                                                        */
+  int inner;              /* 1: the span ends on a chunk boundary inside the recording     */
+  float* chunk_means;     /* phase 1 out: DEVICE fp32 [n_chunks of the span, 128]          */
+  const float* hc;        /* phase 2 in:  DEVICE fp32 [n_chunks of the span, 128]          */
+} ResepSpanCtl;
+int resep_forward_span(ResepHandle* h, const float* mix, int64_t span_len, float* est, void* workspace,
+                       size_t workspace_bytes, int precision, void* stream, const ResepSpanCtl* ctl);
+/* mem_model[0] on one sequence of chunk summaries: chunk_means, hc DEVICE fp32 [n_chunks,128] (may alias). */
+int resep_memory_workspace_bytes(ResepHandle* h, int n_chunks, size_t* bytes);
+int resep_memory_block(ResepHandle* h, const float* chunk_means, float* hc, int n_chunks, void* workspace,
+                       size_t workspace_bytes, int precision, void* stream);
+
 /* Polyphase FIR resampling on the device, for running the 8 kHz separator on the product's 16 kHz audio
  * (api.py:115 feeds 16 kHz to a model whose sample_rate is 8000).  Same arithmetic as
  * torchaudio.functional.resample: x zero-padded by `width` on the left,

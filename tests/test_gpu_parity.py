@@ -521,3 +521,20 @@ def test_bf16_fallback_paths_agree_with_the_default(cuda_lib_built):
         assert si_snr_db(got.permute(0, 2, 1), ref.permute(0, 2, 1)).min().item() > 40.0, k
     for k in ("RESEP_PDL=0", "RESEP_GRAPH=0", "RESEP_MASKDEC=0"):     # same kernels, other launch mechanics: same bits
         assert torch.equal(outs[k], ref), k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_long_recording_split_is_bit_identical(make_sep, prec):
+    """SURVEY 8e (optional row): one recording cut on chunk boundaries into spans that run their intra blocks
+    separately (here one after the other on one GPU; across ranks the same calls with an all_gather in between --
+    tests/test_host.py), the memory transformer on the full sequence of chunk summaries, overlap-add across the
+    cuts.  Every per-chunk kernel is row-local and the memory block sees the same inputs: same bits as one forward."""
+    from clearconverse_b200 import sharding
+    sep = make_sep(prec, "coupled")
+    for T in (60000, 2408, 21616):                     # 50 chunks; L % 150 == 0 (padding chunk); ragged tail
+        mix = synth_mixture(T, 11 + T)[0]
+        want = sep.separate_batch(mix[None])[0]
+        for parts in (1, 2, 3, 7):
+            got = sharding.separate_long(sep, mix, parts=parts)
+            assert got.shape == want.shape
+            assert torch.equal(got, want), (prec, T, parts, (got - want).abs().max().item())

@@ -148,3 +148,84 @@ def test_sharded_driver_world_size_2_gloo():
     ok, total, want = q.get(timeout=120)
     [p.join(60) for p in procs]
     assert ok and total == want and all(p.exitcode == 0 for p in procs)
+
+
+# ---- one long recording split across ranks (SURVEY 8e optional row): host logic with a toy engine
+class _ToyEngine:
+    """Stands in for the CUDA engine with the same phase structure: per-chunk work in the two span phases, a memory
+    step that needs the whole sequence of chunk summaries, and a stride-8 / 16-tap overlap-add 'decoder'."""
+
+    def __init__(self):
+        self.kept = {}
+
+    def span_phase1(self, mix_span, inner, precision, lane=0):
+        n = mix_span.numel()
+        L = (n - 16) // 8 + 1
+        n_chunks = L // 150 if (inner and L % 150 == 0) else L // 150 + 1
+        frames = torch.zeros(n_chunks * 150, 16)
+        frames[:L] = mix_span.unfold(0, 16, 8)[:L]
+        self.kept[lane] = (frames, L)
+        return frames.view(n_chunks, 150 * 16).mean(1, keepdim=True).repeat(1, 128)
+
+    def memory_block(self, means, precision):
+        return means + means.cumsum(0) * 0.01 + means.sum() * 1e-3       # depends on the whole sequence and on order
+
+    def span_phase2(self, span_len, hc, inner, precision, lane=0):
+        frames, L = self.kept[lane]
+        g = 1.0 + hc[:, :1].repeat_interleave(150, 0)                    # [rows, 1]
+        y = frames * g
+        est = torch.zeros(span_len, 2)
+        for l in range(L):
+            est[8 * l:8 * l + 16, 0] += y[l]
+            est[8 * l:8 * l + 16, 1] -= 0.5 * y[l]
+        return est
+
+
+class _ToySep:
+    def __init__(self):
+        self._engine, self.device, self.precision = _ToyEngine(), torch.device("cpu"), "fp32"
+
+
+def _toy_reference(mix):
+    sep = _ToySep()
+    return sharding.separate_long(sep, mix, parts=1)
+
+
+@pytest.mark.parametrize("T", [16, 1208, 2400, 2408, 3616, 20000])
+def test_split_long_covers_every_chunk_once_and_reassembles(T):
+    mix = torch.randn(T, generator=torch.Generator().manual_seed(T))
+    want = _toy_reference(mix)
+    for parts in (1, 2, 3, 5):
+        spans = sharding.split_long(T, parts)
+        assert spans[0][0] == 0 and spans[-1][1] == T and sum(s[3] for s in spans) == sharding.chunks_of(T)
+        for a, b, c0, n, inner in spans:
+            assert b - a >= 16 and a == 1200 * c0 and (not inner or b - a == 1200 * n + 8)
+        got = sharding.separate_long(_ToySep(), mix, parts=parts)
+        assert torch.allclose(got, want, atol=1e-5), (T, parts)
+
+
+def _gloo_long_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mix = torch.randn(20000, generator=torch.Generator().manual_seed(5))
+    got = sharding.separate_long(_ToySep(), mix, rank, world, group=dist.group.WORLD)
+    ok = torch.allclose(got, _toy_reference(mix), atol=1e-5)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(bool(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_long_recording_split_world_size_2_gloo():
+    """The N > 1 path of separate_long: all_gather of the chunk summaries, redundant memory step, all_gather of the span
+    outputs, overlap-add across the cut -- every rank ends up with the unsplit result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_long_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    ok = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert ok and all(p.exitcode == 0 for p in procs)
