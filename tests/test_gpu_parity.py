@@ -538,3 +538,16 @@ def test_long_recording_split_is_bit_identical(make_sep, prec):
             got = sharding.separate_long(sep, mix, parts=parts)
             assert got.shape == want.shape
             assert torch.equal(got, want), (prec, T, parts, (got - want).abs().max().item())
+
+
+def test_separate_stream_with_changing_shapes(make_sep):
+    """The pipelined driver with batch shapes that change from batch to batch (every shape gets its own persistent
+    I/O buffers, workspaces grow per lane, graphs are keyed by shape and address): same results as one call each."""
+    sep = make_sep("bf16", "coupled")
+    shapes = [(2, 4000), (1, 9000), (3, 2000), (2, 4000), (1, 16), (1, 9000), (4, 1211), (2, 4000)]
+    batches = [synth_batch(b, t, 400 + i).pin_memory() for i, (b, t) in enumerate(shapes)]
+    want = [sep.separate_batch(x).cpu() for x in batches]
+    outs = [o.clone() for o in sep.separate_stream(iter(batches), depth=2)]
+    assert len(outs) == len(batches)
+    for o, w in zip(outs, want):
+        assert o.shape == w.shape and torch.equal(o, w)
