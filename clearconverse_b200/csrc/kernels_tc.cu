@@ -756,6 +756,218 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Attention for the tf32 mode (fp32 q / k / v in torch's [q128 | k128 | v128] layout, fp32 ctx out) on the tensor cores
+// at fp32-class accuracy: every operand is split x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits
+// together) and every product takes three bf16 HMMAs, a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (relative error
+// ~2^-16, far below the tf32 GEMMs around it).  12 HMMAs per 16 x 16 block against k_attention_f32's 512 FMAs per
+// thread-row; softmax in fp32 with exact fp32 row sums.  Sequences of at most 160 rows (every intra chunk); longer
+// ones keep the FMA kernel.  Optionally rounds ctx to tf32 (the out-projection GEMM's operand format), which saves
+// the separate rounding pass.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(a, b);
+  const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
+  lo = pack_bf16(a - h.x, b - h.y);
+}
+
+__global__ void __launch_bounds__(160, 3)
+k_attention_split16(const float* __restrict__ qkv, float* __restrict__ ctx, int seq_len, const int* __restrict__ seq_off, int round_out) {
+  constexpr int KMAX = 160, WARPS = 5, MT = 2, THREADS = 160;
+  __shared__ __align__(16) bf16 Kh[KMAX * AS_ROW];
+  __shared__ __align__(16) bf16 Kl[KMAX * AS_ROW];
+  __shared__ __align__(16) bf16 Vh[KMAX * AS_ROW];
+  __shared__ __align__(16) bf16 Vl[KMAX * AS_ROW];
+  __shared__ float s_kmax[WARPS];
+  const int seq = blockIdx.x;
+  int off, len;
+  if (seq_off != nullptr) {
+    off = seq_off[seq];
+    len = seq_off[seq + 1] - off;
+  } else {
+    off = seq * seq_len;
+    len = seq_len;
+  }
+  if (len <= 0) return;
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const float* base = qkv + (int64_t)off * (3 * D) + head * DH;
+  {  // stage K / V rows as hi / lo bf16 (rows past the sequence up to the next multiple of 16 are zero); max squared key norm
+    float kn2max = 0.f;
+    const int kp = (len + 15) & ~15;
+    for (int key = threadIdx.x; key < kp; key += THREADS) {
+      float kv[16], vv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { kv[i] = 0.f; vv[i] = 0.f; }
+      if (key < len) {
+        const float4* pk = reinterpret_cast<const float4*>(base + (int64_t)key * (3 * D) + D);
+        const float4* pv = reinterpret_cast<const float4*>(base + (int64_t)key * (3 * D) + 2 * D);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = __ldg(pk + i), b = __ldg(pv + i);
+          kv[4 * i] = a.x; kv[4 * i + 1] = a.y; kv[4 * i + 2] = a.z; kv[4 * i + 3] = a.w;
+          vv[4 * i] = b.x; vv[4 * i + 1] = b.y; vv[4 * i + 2] = b.z; vv[4 * i + 3] = b.w;
+        }
+      }
+      uint32_t kh[8], kl[8], vh[8], vl[8];
+      float kn2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        split_bf16x2(kv[2 * i], kv[2 * i + 1], kh[i], kl[i]);
+        split_bf16x2(vv[2 * i], vv[2 * i + 1], vh[i], vl[i]);
+        kn2 = fmaf(kv[2 * i], kv[2 * i], kn2);
+        kn2 = fmaf(kv[2 * i + 1], kv[2 * i + 1], kn2);
+      }
+      uint4* d;
+      d = reinterpret_cast<uint4*>(Kh + key * AS_ROW); d[0] = make_uint4(kh[0], kh[1], kh[2], kh[3]); d[1] = make_uint4(kh[4], kh[5], kh[6], kh[7]);
+      d = reinterpret_cast<uint4*>(Kl + key * AS_ROW); d[0] = make_uint4(kl[0], kl[1], kl[2], kl[3]); d[1] = make_uint4(kl[4], kl[5], kl[6], kl[7]);
+      d = reinterpret_cast<uint4*>(Vh + key * AS_ROW); d[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]); d[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+      d = reinterpret_cast<uint4*>(Vl + key * AS_ROW); d[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+      kn2max = fmaxf(kn2max, kn2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kn2max = fmaxf(kn2max, __shfl_xor_sync(0xffffffffu, kn2max, o));
+    if (lane == 0) s_kmax[warp] = kn2max;
+  }
+  __syncthreads();
+  float kmax2 = s_kmax[0];
+#pragma unroll
+  for (int i = 1; i < WARPS; ++i) kmax2 = fmaxf(kmax2, s_kmax[i]);
+  const int nkk = (len + 15) >> 4;
+  constexpr float SC = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
+  const int lm = lane >> 3, lr = lane & 7;
+  const int k_off = ((lm >> 1) * 8 + lr) * AS_ROW + (lm & 1) * 8;   // K: m0/m1 = dh halves of keys 0-7, m2/m3 of keys 8-15
+  const int v_off = ((lm & 1) * 8 + lr) * AS_ROW + (lm >> 1) * 8;   // V^T: m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
+#pragma unroll 1
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row0 = warp * (16 * MT) + mt * 16;
+    if (row0 >= len) break;                            // warp-uniform
+    // Q fragment of the m16k16 A operand: a0 = (row g, k 2t4..), a1 = (row g+8, k 2t4..), a2 = (row g, k 8+2t4..), a3 = (row g+8, ..)
+    uint32_t qh[4], ql[4];
+    float qn0 = 0.f, qn1 = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = row0 + g + hh * 8;
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (r < len) {
+        const float* p = base + (int64_t)r * (3 * D);
+        a = __ldg(reinterpret_cast<const float2*>(p + 2 * t4));
+        b = __ldg(reinterpret_cast<const float2*>(p + 8 + 2 * t4));
+      }
+      split_bf16x2(a.x, a.y, qh[hh], ql[hh]);
+      split_bf16x2(b.x, b.y, qh[hh + 2], ql[hh + 2]);
+      const float n = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+      if (hh == 0) qn0 = n; else qn1 = n;
+    }
+    qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
+    qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
+    // three-term score block: s = q_hi.k_hi + q_hi.k_lo + q_lo.k_hi for keys [16 kk, 16 kk + 16)
+    auto scores = [&](int kk, float (&s0)[4], float (&s1)[4]) {
+      uint32_t kh[4], kl[4];
+      ldmatrix_x4(kh, Kh + k_off + kk * 16 * AS_ROW);
+      ldmatrix_x4(kl, Kl + k_off + kk * 16 * AS_ROW);
+      mma_bf16_16816_z(s0, qh, kl[0], kl[1]);
+      mma_bf16_16816_z(s1, qh, kl[2], kl[3]);
+      mma_bf16_16816(s0, ql, kh[0], kh[1]);
+      mma_bf16_16816(s1, ql, kh[2], kh[3]);
+      mma_bf16_16816(s0, qh, kh[0], kh[1]);
+      mma_bf16_16816(s1, qh, kh[2], kh[3]);
+    };
+    // softmax stabiliser from the Cauchy-Schwarz bound (see k_attention_bf16_short); exact row maxima as fallback
+    float mx0 = sqrtf(qn0 * kmax2) * 1.0001f, mx1 = sqrtf(qn1 * kmax2) * 1.0001f;
+    const bool big = !(mx0 * 0.5f < 80.f) || !(mx1 * 0.5f < 80.f);
+    if (__any_sync(0xffffffffu, big)) {
+      mx0 = -INFINITY; mx1 = -INFINITY;
+#pragma unroll 1
+      for (int kk = 0; kk < nkk; ++kk) {
+        float s0[4], s1[4];
+        scores(kk, s0, s1);
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+        if (c + 1 >= len) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+        if (c + 8 >= len) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
+        if (c + 9 >= len) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1])));
+        mx1 = fmaxf(mx1, fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3])));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    }
+    const float nb0 = -mx0 * SC, nb1 = -mx1 * SC;
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+    for (int kk = 0; kk < nkk; ++kk) {
+      float s0[4], s1[4];
+      scores(kk, s0, s1);
+      s0[0] = ex2_approx(fmaf(s0[0], SC, nb0)); s0[1] = ex2_approx(fmaf(s0[1], SC, nb0));
+      s0[2] = ex2_approx(fmaf(s0[2], SC, nb1)); s0[3] = ex2_approx(fmaf(s0[3], SC, nb1));
+      s1[0] = ex2_approx(fmaf(s1[0], SC, nb0)); s1[1] = ex2_approx(fmaf(s1[1], SC, nb0));
+      s1[2] = ex2_approx(fmaf(s1[2], SC, nb1)); s1[3] = ex2_approx(fmaf(s1[3], SC, nb1));
+      if (kk == nkk - 1) {                             // only the last block can hold keys past the sequence
+        const int c = kk * 16 + 2 * t4;
+        if (c >= len) { s0[0] = 0.f; s0[2] = 0.f; }
+        if (c + 1 >= len) { s0[1] = 0.f; s0[3] = 0.f; }
+        if (c + 8 >= len) { s1[0] = 0.f; s1[2] = 0.f; }
+        if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
+      }
+      l0 += (s0[0] + s0[1]) + (s1[0] + s1[1]);
+      l1 += (s0[2] + s0[3]) + (s1[2] + s1[3]);
+      uint32_t ph[4], pl[4];
+      split_bf16x2(s0[0], s0[1], ph[0], pl[0]);
+      split_bf16x2(s0[2], s0[3], ph[1], pl[1]);
+      split_bf16x2(s1[0], s1[1], ph[2], pl[2]);
+      split_bf16x2(s1[2], s1[3], ph[3], pl[3]);
+      uint32_t vh[4], vl[4];
+      ldmatrix_x4_trans(vh, Vh + v_off + kk * 16 * AS_ROW);
+      ldmatrix_x4_trans(vl, Vl + v_off + kk * 16 * AS_ROW);
+      mma_bf16_16816(o0, ph, vl[0], vl[1]);
+      mma_bf16_16816(o1, ph, vl[2], vl[3]);
+      mma_bf16_16816(o0, pl, vh[0], vh[1]);
+      mma_bf16_16816(o1, pl, vh[2], vh[3]);
+      mma_bf16_16816(o0, ph, vh[0], vh[1]);
+      mma_bf16_16816(o1, ph, vh[2], vh[3]);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    float r[8] = {o0[0] * i0, o0[1] * i0, o1[0] * i0, o1[1] * i0, o0[2] * i1, o0[3] * i1, o1[2] * i1, o1[3] * i1};
+    if (round_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = round_tf32(r[i]);
+    }
+    const int r0 = row0 + g, r1 = row0 + g + 8;
+    if (r0 < len) {
+      float* op = ctx + (int64_t)(off + r0) * D + head * DH + 2 * t4;
+      *reinterpret_cast<float2*>(op) = make_float2(r[0], r[1]);
+      *reinterpret_cast<float2*>(op + 8) = make_float2(r[2], r[3]);
+    }
+    if (r1 < len) {
+      float* op = ctx + (int64_t)(off + r1) * D + head * DH + 2 * t4;
+      *reinterpret_cast<float2*>(op) = make_float2(r[4], r[5]);
+      *reinterpret_cast<float2*>(op + 8) = make_float2(r[6], r[7]);
+    }
+  }
+}
+
+// tf32-mode attention: tensor cores for sequences <= 160 rows, the FMA kernel otherwise.  `rounded` tells the caller
+// whether ctx already is in tf32.
+static int launch_attention_tf32mode(ResepHandle* h, const float* qkv, float* ctx, int n_seq, int seq_len, const int* seq_off,
+                                     const int* tile_seq, const int* tile_q0, int n_tiles, int max_len, cudaStream_t st, bool* rounded) {
+  static const bool use_split = !(getenv("RESEP_ATTN_SPLIT16") && getenv("RESEP_ATTN_SPLIT16")[0] == '0');
+  const int longest = seq_off == nullptr ? seq_len : max_len;
+  *rounded = false;
+  if (!use_split || longest > 160) return launch_attention_f32(h, qkv, ctx, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st);
+  if (n_seq == 0) return RESEP_OK;
+  ProfScope prof_scope(h, "k_attention_split16", st);
+  k_attention_split16<<<dim3((unsigned)n_seq, NH), 160, 0, st>>>(qkv, ctx, seq_len, seq_off, 1);
+  RESEP_LAUNCH_CHECK(h, "k_attention_split16");
+  *rounded = true;
+  return RESEP_OK;
+}
+
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
                                  const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st) {
   const int longest = tile_seq == nullptr ? seq_len : max_len;
@@ -885,8 +1097,9 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
   // to tf32 (cvt.rna) first and the weights were rounded on upload.
   if ((rc = launch_layernorm_tf32(h, o, lw.norm1_w, lw.norm1_b, y, rows, st))) return rc;
   if ((rc = launch_gemm_tc<float, EPI_STORE_F32, true>(h, y, lw.in_w_tf, lw.in_b, qkv, rows, 3 * D, D, false, st, lw.in_w_lo))) return rc;
-  if ((rc = launch_attention_f32(h, qkv, ctx, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, st))) return rc;
-  if ((rc = launch_round_tf32(h, ctx, rows * D, st))) return rc;
+  bool ctx_rounded = false;
+  if ((rc = launch_attention_tf32mode(h, qkv, ctx, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st, &ctx_rounded))) return rc;
+  if (!ctx_rounded && (rc = launch_round_tf32(h, ctx, rows * D, st))) return rc;
   if ((rc = launch_gemm_tc<float, EPI_RESID_F32, true>(h, ctx, lw.out_w_tf, lw.out_b, o, rows, D, D, false, st, lw.out_w_lo))) return rc;
   if ((rc = launch_layernorm_tf32(h, o, lw.norm2_w, lw.norm2_b, y, rows, st))) return rc;
   if ((rc = launch_gemm_tc<float, EPI_STORE_TF32, true>(h, y, lw.f1_w_tf, lw.f1_b, hid, rows, FFN, D, true, st, lw.f1_w_lo))) return rc;
