@@ -475,7 +475,9 @@ class SepformerSeparation:
         no throughput.  ``batches``: iterable of [B,T] float32 CPU tensors (pinned for truly asynchronous copies);
         ``out_buffers``: optional list of >= ``depth`` pinned [B,T,n_spk] tensors to reuse (a yielded tensor is
         overwritten ``depth`` batches later).  Batches that already live on the device are taken as they are (no host
-        copy); ``device_out=True`` yields device tensors (new ones, owned by the caller) instead of host tensors."""
+        copy); ``device_out=True`` yields device tensors (new ones, owned by the caller) instead of host tensors.  A batch
+        may also be a LIST of 1-D segments of different lengths (device or pinned host): it is separated with per-item
+        semantics like ``separate_segments`` and yields a list of [T_i, n_spk] device tensors."""
         dev = self.device
         # Two compute streams, batches alternating between them (each lane has its own workspace and CUDA graphs): a
         # forward spends ~12 % of its time in the memory transformer, whose 24 latency-bound launches use 4-56 CTAs;
@@ -494,10 +496,34 @@ class SepformerSeparation:
             return out
 
         for i, mix in enumerate(batches):
+            slot = i % depth
+            compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
+            if isinstance(mix, (list, tuple)):
+                # a ragged batch of 1-D segments (per-item semantics, as separate_segments): results stay on the device
+                segs = [s_.reshape(-1) for s_ in mix]
+                for s_ in segs:
+                    if s_.dtype != torch.float32 or s_.numel() < KERNEL_SIZE:
+                        raise RuntimeError("expected float32 segments of at least 16 samples")
+                lens = [int(s_.numel()) for s_ in segs]
+                offs = [0] * len(lens)
+                for j in range(1, len(lens)):
+                    offs[j] = offs[j - 1] + lens[j - 1]
+                total = offs[-1] + lens[-1]
+                mix_buf, _ = self._engine.static_io(offs, lens, total, slot)
+                with torch.cuda.stream(compute):
+                    for o_, n_, s_ in zip(offs, lens, segs):
+                        mix_buf[o_:o_ + n_].copy_(s_, non_blocking=True)
+                    est = torch.ops.clearconverse_b200.resep_separate_static(
+                        mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT, slot)
+                    res = est.clone()
+                    fin = torch.cuda.Event(); fin.record(compute)
+                inflight.append((fin, [res[2 * o_:2 * (o_ + n_)].view(n_, NUM_SPKS) for o_, n_ in zip(offs, lens)]))
+                if len(inflight) >= depth:
+                    yield drain_one()
+                continue
             self._check_mix(mix)
             B, T = mix.shape
-            offs, lens, slot = [b * T for b in range(B)], [T] * B, i % depth
-            compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
+            offs, lens = [b * T for b in range(B)], [T] * B
             # slot i % depth was last used by batch i - depth, whose result has been drained (synchronised) already
             mix_buf, _ = self._engine.static_io(offs, lens, B * T, slot)
             if mix.is_cuda:

@@ -98,22 +98,33 @@ def plan_shards(lens: list[int], world_size: int, max_chunks_per_batch: int = 20
 
 
 def separate_sharded(segments, separate_fn, rank: int = 0, world_size: int = 1, group=None,
-                     max_chunks_per_batch: int = 2048, gather: bool = True):
+                     max_chunks_per_batch: int = 2048, gather: bool = True, pipeline=None):
     """Run this rank's share of ``segments`` (list of 1-D float32 tensors) through
     ``separate_fn(list_of_segments) -> list of [T_i, n_spk] tensors`` and, if ``gather``,
     collect all results on rank 0 in the original order (host-side gather, no NCCL).
+
+    ``pipeline`` (optional): a callable taking an iterable of segment lists and yielding the result lists in order
+    (``SepformerSeparation.separate_stream``): this rank's batches then run through it, two in flight, instead of
+    one ``separate_fn`` call after the other.
 
     Returns (results or None on non-zero ranks, audio samples this rank processed)."""
     lens = [int(s.numel()) for s in segments]
     batches, per_rank = plan_shards(lens, world_size, max_chunks_per_batch)
     mine: dict[int, object] = {}
     samples = 0
-    for b in per_rank[rank]:
-        idx = batches[b].indices
-        outs = separate_fn([segments[i] for i in idx])
-        for i, o in zip(idx, outs):
-            mine[i] = o
-            samples += lens[i]
+    if pipeline is not None:
+        mine_batches = [batches[b].indices for b in per_rank[rank]]
+        for idx, outs in zip(mine_batches, pipeline([segments[i] for i in idx] for idx in mine_batches)):
+            for i, o in zip(idx, outs):
+                mine[i] = o
+                samples += lens[i]
+    else:
+        for b in per_rank[rank]:
+            idx = batches[b].indices
+            outs = separate_fn([segments[i] for i in idx])
+            for i, o in zip(idx, outs):
+                mine[i] = o
+                samples += lens[i]
     if not gather:
         return mine, samples
     if world_size == 1:

@@ -551,3 +551,21 @@ def test_separate_stream_with_changing_shapes(make_sep):
     assert len(outs) == len(batches)
     for o, w in zip(outs, want):
         assert o.shape == w.shape and torch.equal(o, w)
+
+
+def test_ragged_batches_through_the_pipelined_driver(make_sep):
+    """separate_stream with LISTS of segments (ragged batches, per-item semantics) and the sharded driver's `pipeline`
+    hook: same bits as separate_segments batch by batch."""
+    from clearconverse_b200 import sharding
+    sep = make_sep("bf16", "independent")
+    lens = [4000, 16, 9000, 1211, 32000, 2500, 8000, 700, 12000, 5000]
+    segs = [synth_mixture(n, 500 + i)[0].cuda() for i, n in enumerate(lens)]
+    groups = [segs[0:3], segs[3:4], segs[4:8], segs[8:10]]
+    want = [sep.separate_segments(g) for g in groups]
+    got = list(sep.separate_stream(iter(groups), depth=2))
+    assert len(got) == len(groups)
+    for g_, w_ in zip(got, want):
+        assert len(g_) == len(w_) and all(torch.equal(a, b) for a, b in zip(g_, w_))
+    res_a, n_a = sharding.separate_sharded(segs, sep.separate_segments, 0, 1, max_chunks_per_batch=40)
+    res_b, n_b = sharding.separate_sharded(segs, sep.separate_segments, 0, 1, max_chunks_per_batch=40, pipeline=sep.separate_stream)
+    assert n_a == n_b == sum(lens) and all(torch.equal(a, b) for a, b in zip(res_a, res_b))
