@@ -380,7 +380,7 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
                         float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                         cudaStream_t st, const ResepDebugOut* dbg) {
   if (!h) return RESEP_EINVAL;
-  if (dbg != nullptr || h->prof_on || !h->use_graphs || precision != RESEP_PREC_BF16 || !mix || !item_off || !item_len || !est || B <= 0)
+  if (dbg != nullptr || h->prof_on || !h->use_graphs || !mix || !item_off || !item_len || !est || B <= 0)
     return forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, dbg);
   std::vector<uint64_t> key;
   key.reserve(6 + 2 * (size_t)B);
