@@ -1,4 +1,4 @@
-"""Small bf16 / tf32 / fp32 forwards + the 8f ops, as a target for compute-sanitizer (memcheck / racecheck / initcheck)."""
+"""Small bf16 / tf32 / fp32 forwards + the 8f ops, as a quick all-modes smoke (compute-sanitizer is not available on this pool)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("RESEP_GRAPH", "0")
