@@ -229,3 +229,16 @@ def test_long_recording_split_world_size_2_gloo():
     ok = q.get(timeout=120)
     [p.join(60) for p in procs]
     assert ok and all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.parametrize("orig,new", [(16000, 8000), (8000, 16000), (44100, 8000), (8000, 48000), (48000, 16000)])
+def test_resample_taps_equal_torchaudio(orig, new):
+    """The FIR taps handed to resep_resample_fir are torchaudio.functional.resample's windowed sinc, bit for bit."""
+    import math
+    ta = pytest.importorskip("torchaudio")
+    from clearconverse_b200.separation import resample_taps
+    g = math.gcd(orig, new)
+    want, width = ta.functional.functional._get_sinc_resample_kernel(orig, new, g)
+    taps, w, o, n = resample_taps(orig, new)
+    assert (w, o, n) == (width, orig // g, new // g)
+    assert torch.equal(taps, want.reshape(taps.shape))
