@@ -160,15 +160,31 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
 }
 
 // ------------------------------------------------------------------------------ plans
-static void free_plan(Plan* p) {
+static void free_plan(Plan* p) {   // handle teardown only: releases the blocks for real
   if (!p) return;
   if (p->dev) cudaFree(p->dev);
+  if (p->host) cudaFreeHost(p->host);
   delete p;
 }
 
-static void drop_graphs_of(ResepHandle* h) {
-  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  h->graphs.clear();
+// Eviction: the plan's blocks go back to the handle's pool.  Work already enqueued that reads the device tables is
+// safe: a block is only rewritten by a later plan's upload, which is stream-ordered behind that work on the same
+// stream, and a handle is thread-compatible (one caller at a time).  Lanes on OTHER streams keep their plans alive by
+// using them (LRU), and the table is large enough (64) that a plan evicted here has not been launched for 63 shapes.
+static void recycle_plan(ResepHandle* h, Plan* p) {
+  if (!p) return;
+  if (p->dev && p->host) h->plan_pool.push_back({p->dev, p->host, p->cap_bytes});
+  else { if (p->dev) cudaFree(p->dev); if (p->host) cudaFreeHost(p->host); }
+  delete p;
+}
+
+static void drop_graphs_of(ResepHandle* h, const Plan* plan = nullptr) {   // plan == nullptr: every graph
+  for (size_t i = 0; i < h->graphs.size();) {
+    if (plan == nullptr || h->graphs[i].plan == plan || h->graphs[i].plan == nullptr) {
+      if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+      h->graphs.erase(h->graphs.begin() + i);
+    } else ++i;
+  }
 }
 
 static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_t* item_len, int batch_mode,
@@ -262,9 +278,27 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
   const size_t o_dti = put(dec_tile_item.data(), sizeof(int) * dec_tile_item.size());
   const size_t o_dts = put(dec_tile_slot0.data(), sizeof(int) * dec_tile_slot0.size());
   p->dev_bytes = blob.size();
-  cudaError_t e = cudaMalloc(&p->dev, p->dev_bytes);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->dev, blob.data(), blob.size(), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // blob is a stack-lifetime pageable buffer
+  size_t cap = 4096;
+  while (cap < blob.size()) cap <<= 1;
+  p->cap_bytes = cap;
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < h->plan_pool.size(); ++i)
+    if (h->plan_pool[i].cap == cap) {
+      p->dev = h->plan_pool[i].dev; p->host = h->plan_pool[i].host;
+      h->plan_pool.erase(h->plan_pool.begin() + i);
+      break;
+    }
+  if (!p->dev) {
+    e = cudaMalloc(&p->dev, cap);
+    if (e == cudaSuccess) e = cudaMallocHost(&p->host, cap);
+  }
+  if (e == cudaSuccess) {
+    // pinned staging owned by the plan: the copy is truly asynchronous and needs no stream synchronisation.  A
+    // recycled host block may still be the source of its previous plan's upload only if that upload has not run
+    // yet -- it was enqueued at least 63 plans ago on a stream this handle has launched whole forwards on since.
+    std::memcpy(p->host, blob.data(), blob.size());
+    e = cudaMemcpyAsync(p->dev, p->host, blob.size(), cudaMemcpyHostToDevice, st);
+  }
   if (e != cudaSuccess) {
     free_plan(p);
     return set_err(h, RESEP_ECUDA, std::string("plan upload: ") + cudaGetErrorString(e));
@@ -283,11 +317,11 @@ static int get_plan(ResepHandle* h, int B, const int64_t* item_off, const int64_
   p->d_dec_tile_item = reinterpret_cast<const int*>(base + o_dti);
   p->d_dec_tile_slot0 = reinterpret_cast<const int*>(base + o_dts);
   p->last_use = h->tick;
-  if (h->plans.size() >= 16) {   // evict the least recently used plan (stream-ordered free is safe: cudaFree syncs)
-    drop_graphs_of(h);             // captured graphs hold pointers into plan tables
+  if (h->plans.size() >= 64) {   // evict the least recently used plan; only the graphs captured over ITS tables go with it
     auto it = std::min_element(h->plans.begin(), h->plans.end(),
                                [](const Plan* a, const Plan* b) { return a->last_use < b->last_use; });
-    free_plan(*it);
+    drop_graphs_of(h, *it);
+    recycle_plan(h, *it);
     h->plans.erase(it);
   }
   h->plans.push_back(p);
@@ -370,9 +404,16 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
                          float* est, void* workspace, size_t workspace_bytes, int precision, int batch_mode,
                          cudaStream_t st, const ResepDebugOut* dbg, const ResepSpanCtl* span = nullptr);
 
-static void drop_graphs(ResepHandle* h) {
-  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  h->graphs.clear();
+static void drop_graphs(ResepHandle* h) { drop_graphs_of(h); }
+
+static const Plan* find_plan(const ResepHandle* h, int B, const int64_t* item_off, const int64_t* item_len, int batch_mode) {
+  for (const Plan* p : h->plans) {
+    if (p->B != B || p->key.size() != 2 + 2 * (size_t)B || p->key[1] != batch_mode) continue;
+    bool same = true;
+    for (int i = 0; i < B && same; ++i) same = p->key[2 + 2 * i] == item_off[i] && p->key[3 + 2 * i] == item_len[i];
+    if (same) return p;
+  }
+  return nullptr;
 }
 
 // Forward pass, replayed from a CUDA graph when the same (shapes, buffers, mode) has been seen before.
@@ -400,13 +441,14 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
   if (!rec) {   // first sighting: run eagerly and remember the key
     int rc = forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, nullptr);
     if (rc) return rc;
-    if (h->graphs.size() >= 12) {
+    if (h->graphs.size() >= 48) {
       auto it = std::min_element(h->graphs.begin(), h->graphs.end(), [](const ResepHandle::GraphRec& a, const ResepHandle::GraphRec& b) { return a.last_use < b.last_use; });
       if (it->exec) cudaGraphExecDestroy(it->exec);
       h->graphs.erase(it);
     }
     ResepHandle::GraphRec g;
     g.key = key; g.last_use = h->tick;
+    g.plan = find_plan(h, B, item_off, item_len, batch_mode);
     h->graphs.push_back(g);
     return RESEP_OK;
   }
@@ -427,12 +469,12 @@ static int forward_impl(ResepHandle* h, const float* mix, const int64_t* item_of
   if (e != cudaSuccess || rc != RESEP_OK || !exec) {   // capture failed: run eagerly; give up on graphs after three failures
     cudaGetLastError();
     h->launches = l0;
-    static int failures = 0;
-    if (++failures >= 3) h->use_graphs = 0;
+    if (++h->graph_failures >= 3) h->use_graphs = 0;   // per handle: another handle's trouble does not switch this one's graphs off
     drop_graphs(h);
     return forward_eager(h, mix, item_off, item_len, B, est, workspace, workspace_bytes, precision, batch_mode, st, nullptr);
   }
   rec->exec = exec;
+  rec->plan = find_plan(h, B, item_off, item_len, batch_mode);   // (the plan may have been re-created since the first sighting)
   rec->launches = h->launches - l0;
   rec->last_use = h->tick;
   RESEP_CUDA(h, cudaGraphLaunch(exec, st));
@@ -594,6 +636,7 @@ int resep_destroy(ResepHandle* h) {
   drop_graphs_of(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (Plan* p : h->plans) free_plan(p);
+  for (auto& b : h->plan_pool) { cudaFree(b.dev); cudaFreeHost(b.host); }
   if (h->arena) cudaFree(h->arena);
   delete h;
   return RESEP_OK;

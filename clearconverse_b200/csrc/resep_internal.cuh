@@ -71,9 +71,12 @@ struct Plan {
   // k_maskdec_tc (fused output_fc + decoder) needs a token row for every output slot of every item (8 * 150 * S >= T:
   // false only when L % 150 == 149 and T % 8 != 0) and sample offsets that fit an int
   bool maskdec_ok = false;
-  // one device allocation holding every table below
+  // one device block holding every table below, and the pinned host block it is uploaded from (both come from the
+  // handle's size-class pools and go back there on eviction: no cudaMalloc / cudaFree / stream sync per new shape)
   void* dev = nullptr;
-  size_t dev_bytes = 0;
+  void* host = nullptr;
+  size_t dev_bytes = 0;     // bytes used
+  size_t cap_bytes = 0;     // size class of the blocks
   const int64_t* d_item_off = nullptr;    // [B] sample offset of item in mix
   const int64_t* d_item_len = nullptr;    // [B] T
   const int* d_item_L = nullptr;          // [B] frames
@@ -116,10 +119,14 @@ struct ResepHandle {
     int64_t launches = 0;
     uint64_t last_use = 0;
     bool seen_only = true;   // first sighting runs eagerly (plans, attributes and occupancy queries are set up outside capture)
+    const resep::Plan* plan = nullptr;   // the captured kernels hold pointers into this plan's device tables
   };
   std::vector<GraphRec> graphs;
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's stream may be the legacy default stream)
   int use_graphs = 1;                  // RESEP_GRAPH=0 disables
+  int graph_failures = 0;              // capture / instantiate failures of THIS handle; three switch its graphs off
+  struct PoolBlock { void* dev; void* host; size_t cap; };
+  std::vector<PoolBlock> plan_pool;    // free (device, pinned host) block pairs of evicted plans, reused by size class
   bool tc_ready = false;  // tensor maps for the tcgen05 path built
   void* tc_state = nullptr;
 };

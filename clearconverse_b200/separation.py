@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 from collections import namedtuple
 from types import SimpleNamespace
 
@@ -30,10 +31,23 @@ KERNEL_SIZE = 16
 _IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
 
 # ---------------------------------------------------------------------------------------------
-# engine registry: the custom op takes an integer engine id (ops cannot carry Python objects)
-_ENGINES: dict[int, "_Engine"] = {}
+# engine registry: the custom op takes an integer engine id (ops cannot carry Python objects).  Weak values: the
+# registry must not keep an engine (its device weights, workspaces, static I/O buffers, CUDA graphs) alive once the
+# separator that owns it has been dropped -- upstream's object frees its memory when it goes out of scope.
+_ENGINES: "weakref.WeakValueDictionary[int, _Engine]" = weakref.WeakValueDictionary()
 _ENGINES_LOCK = threading.Lock()
 _NEXT_ID = [1]
+# The blocking calls (separate_batch / separate_segments) own this workspace lane and static-I/O slot; the lanes of
+# the pipelined driver are 0 and 1, its slots 0 .. depth-1.  Keeping the namespaces apart means a separate_batch
+# issued on the caller's stream while a separate_stream generator is half consumed (or was abandoned) never touches
+# a buffer or workspace that a lane stream may still be using.
+SYNC_LANE = "sync"
+
+
+def _destroy_handle(lib, handle):
+    if handle is not None and handle.value:
+        lib.resep_destroy(handle)
+        handle.value = None
 
 
 class _Engine:
@@ -58,6 +72,8 @@ class _Engine:
             self.id = _NEXT_ID[0]
             _NEXT_ID[0] += 1
             _ENGINES[self.id] = self
+        # belt and braces next to __del__: runs at interpreter exit too, and never resurrects the engine
+        self._finalizer = weakref.finalize(self, _destroy_handle, self.lib, self.handle)
 
     def reload(self, sds: dict, pe_rows: int):
         packed = _weights.PackedWeights(sds, pe_rows)
@@ -84,7 +100,13 @@ class _Engine:
         io = self._static_io.get(key)
         if io is None:
             if len(self._static_io) >= 24:
-                self._static_io.pop(next(iter(self._static_io)))
+                old_key = next(iter(self._static_io))
+                old = self._static_io.pop(old_key)
+                if old_key[3] == SYNC_LANE:               # used on the caller's stream only
+                    for t in old:
+                        t.record_stream(torch.cuda.current_stream(self.device))
+                else:                                     # a pipeline slot: its lane stream may still be using it
+                    torch.cuda.synchronize(self.device)
             with torch.cuda.device(self.device):
                 io = (torch.empty(total, dtype=torch.float32, device=self.device),
                       torch.zeros(2 * total, dtype=torch.float32, device=self.device))
@@ -92,7 +114,7 @@ class _Engine:
         return io
 
     def forward(self, mix_flat: torch.Tensor, offs: list[int], lens: list[int], precision: int, batch_mode: int,
-                debug: dict | None = None, out: torch.Tensor | None = None, lane: int = 0) -> torch.Tensor:
+                debug: dict | None = None, out: torch.Tensor | None = None, lane=SYNC_LANE) -> torch.Tensor:
         """mix_flat: 1-D fp32 CUDA tensor holding every item; returns est_flat [2 * mix_flat.numel()]
         (``out`` if given: it must be zero-filled where items leave gaps).  Forwards that may be in flight at the same
         time (different CUDA streams) must use different ``lane``s: a lane owns a workspace."""
@@ -199,9 +221,12 @@ class _Engine:
         return peaks
 
     def close(self):
-        if getattr(self, "handle", None) and self.handle.value:
-            self.lib.resep_destroy(self.handle)
-            self.handle = C.c_void_p()
+        fin = getattr(self, "_finalizer", None)
+        if fin is not None and fin.alive:
+            fin()                                     # resep_destroy, exactly once
+        self.handle = C.c_void_p()
+        self.workspaces = {}
+        self._static_io = {}
         with _ENGINES_LOCK:
             _ENGINES.pop(getattr(self, "id", -1), None)
 
@@ -231,6 +256,29 @@ def resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, 
     return kernels.to(torch.float32).reshape(new, -1).contiguous(), width, orig, new
 
 
+def _load_audio(path: str):
+    """(waveform [channels, T] float32 in [-1, 1], sample rate).  ``torchaudio.load`` as upstream; torchaudio >= 2.9
+    needs the optional torchcodec package for that, so PCM / float WAV files fall back to scipy's reader."""
+    try:
+        import torchaudio
+        return torchaudio.load(path)
+    except (ImportError, RuntimeError, OSError):
+        pass
+    import numpy as np
+    from scipy.io import wavfile
+    fs, data = wavfile.read(path)
+    if data.dtype == np.int16:
+        x = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        x = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    x = torch.from_numpy(np.ascontiguousarray(x))
+    return (x[None] if x.dim() == 1 else x.T.contiguous()), int(fs)
+
+
 def _needs_zero_fill(offs, lens, total) -> bool:
     """True when the items do not tile the flat buffer exactly (gaps would stay uninitialised)."""
     pos = 0
@@ -249,9 +297,9 @@ def _resep_separate(mix_flat: torch.Tensor, offs: list[int], lens: list[int], en
     eng = _ENGINES.get(engine)
     if eng is None:
         raise RuntimeError("clearconverse_b200: separator engine was destroyed")
-    mix_buf, est_buf = eng.static_io(offs, lens, mix_flat.numel())
+    mix_buf, est_buf = eng.static_io(offs, lens, mix_flat.numel(), SYNC_LANE)
     mix_buf.copy_(mix_flat)
-    eng.forward(mix_buf, offs, lens, precision, batch_mode, out=est_buf)
+    eng.forward(mix_buf, offs, lens, precision, batch_mode, out=est_buf, lane=SYNC_LANE)
     return est_buf.clone()                      # a new tensor owned by the caller, as upstream returns
 
 
@@ -480,14 +528,15 @@ class SepformerSeparation:
         semantics like ``separate_segments`` and yields a list of [T_i, n_spk] device tensors."""
         dev = self.device
         # Two compute streams, batches alternating between them (each lane has its own workspace and CUDA graphs): a
-        # forward spends ~12 % of its time in the memory transformer, whose 24 latency-bound launches use 4-56 CTAs;
+        # forward spends ~12 % of its time in the memory transformer, whose latency-bound launches use few CTAs;
         # the neighbouring batch's intra block fills those SMs (scripts/gpu_timeline.py, scripts/gpu_dual_stream.py).
         if getattr(self, "_pipe_streams", None) is None:   # created once: the caching allocator keeps per-stream pools,
             self._pipe_streams = [torch.cuda.Stream(dev) for _ in range(4)]   # fresh streams mean fresh cudaMallocs
-        lanes = self._pipe_streams[:2] if depth >= 2 else [torch.cuda.current_stream(dev)]
+        lanes = self._pipe_streams[:2] if depth >= 2 else [self._pipe_streams[0]]
         h2d, d2h = self._pipe_streams[2], self._pipe_streams[3]
+        caller = torch.cuda.current_stream(dev)
         for st in self._pipe_streams:
-            st.wait_stream(torch.cuda.current_stream(dev))
+            st.wait_stream(caller)
         inflight = []                                     # (event, host_out)
 
         def drain_one():
@@ -495,71 +544,83 @@ class SepformerSeparation:
             ev.synchronize()
             return out
 
-        for i, mix in enumerate(batches):
-            slot = i % depth
-            compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
-            if isinstance(mix, (list, tuple)):
-                # a ragged batch of 1-D segments (per-item semantics, as separate_segments): results stay on the device
-                segs = [s_.reshape(-1) for s_ in mix]
-                for s_ in segs:
-                    if s_.dtype != torch.float32 or s_.numel() < KERNEL_SIZE:
-                        raise RuntimeError("expected float32 segments of at least 16 samples")
-                lens = [int(s_.numel()) for s_ in segs]
-                offs = [0] * len(lens)
-                for j in range(1, len(lens)):
-                    offs[j] = offs[j - 1] + lens[j - 1]
-                total = offs[-1] + lens[-1]
-                mix_buf, _ = self._engine.static_io(offs, lens, total, slot)
+        def hand_over(t):
+            # device results are allocated from the lane stream's pool but consumed on the caller's stream: tell the
+            # caching allocator, or the block could be handed out again on the lane under a pending reader
+            t.record_stream(caller)
+            return t
+
+        try:
+            for i, mix in enumerate(batches):
+                slot = i % depth
+                compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
+                if isinstance(mix, (list, tuple)):
+                    # a ragged batch of 1-D segments (per-item semantics, as separate_segments): results stay on the device
+                    segs = [s_.reshape(-1) for s_ in mix]
+                    for s_ in segs:
+                        if s_.dtype != torch.float32 or s_.numel() < KERNEL_SIZE:
+                            raise RuntimeError("expected float32 segments of at least 16 samples")
+                    lens = [int(s_.numel()) for s_ in segs]
+                    offs = [0] * len(lens)
+                    for j in range(1, len(lens)):
+                        offs[j] = offs[j - 1] + lens[j - 1]
+                    total = offs[-1] + lens[-1]
+                    mix_buf, _ = self._engine.static_io(offs, lens, total, slot)
+                    with torch.cuda.stream(compute):
+                        for o_, n_, s_ in zip(offs, lens, segs):
+                            mix_buf[o_:o_ + n_].copy_(s_, non_blocking=True)
+                        est = torch.ops.clearconverse_b200.resep_separate_static(
+                            mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT, slot)
+                        res = hand_over(est.clone())
+                        fin = torch.cuda.Event(); fin.record(compute)
+                    inflight.append((fin, [res[2 * o_:2 * (o_ + n_)].view(n_, NUM_SPKS) for o_, n_ in zip(offs, lens)]))
+                    if len(inflight) >= depth:
+                        yield drain_one()
+                    continue
+                self._check_mix(mix)
+                B, T = mix.shape
+                offs, lens = [b * T for b in range(B)], [T] * B
+                # slot i % depth was last used by batch i - depth, whose result has been drained (synchronised) already
+                mix_buf, _ = self._engine.static_io(offs, lens, B * T, slot)
+                if mix.is_cuda:
+                    with torch.cuda.stream(compute):
+                        mix_buf.copy_(mix.reshape(-1), non_blocking=True)
+                else:
+                    with torch.cuda.stream(h2d):
+                        mix_buf.copy_(mix.reshape(-1), non_blocking=True)
+                        up = torch.cuda.Event(); up.record(h2d)
+                    compute.wait_event(up)
                 with torch.cuda.stream(compute):
-                    for o_, n_, s_ in zip(offs, lens, segs):
-                        mix_buf[o_:o_ + n_].copy_(s_, non_blocking=True)
                     est = torch.ops.clearconverse_b200.resep_separate_static(
-                        mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision], _lib.BATCH_INDEPENDENT, slot)
-                    res = est.clone()
-                    fin = torch.cuda.Event(); fin.record(compute)
-                inflight.append((fin, [res[2 * o_:2 * (o_ + n_)].view(n_, NUM_SPKS) for o_, n_ in zip(offs, lens)]))
+                        mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision],
+                        _lib.BATCH_MODES[self.batch_mode], slot).view(B, T, NUM_SPKS)
+                if device_out:
+                    with torch.cuda.stream(compute):
+                        res = hand_over(est.clone())
+                        fin = torch.cuda.Event(); fin.record(compute)
+                    inflight.append((fin, res))
+                    if len(inflight) >= depth:
+                        yield drain_one()
+                    continue
+                done = torch.cuda.Event(); done.record(compute)
+                if out_buffers is not None:
+                    host = out_buffers[i % len(out_buffers)]
+                else:
+                    host = torch.empty(B, T, NUM_SPKS, dtype=torch.float32).pin_memory()
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    host.copy_(est, non_blocking=True)
+                    down = torch.cuda.Event(); down.record(d2h)
+                inflight.append((down, host))
                 if len(inflight) >= depth:
                     yield drain_one()
-                continue
-            self._check_mix(mix)
-            B, T = mix.shape
-            offs, lens = [b * T for b in range(B)], [T] * B
-            # slot i % depth was last used by batch i - depth, whose result has been drained (synchronised) already
-            mix_buf, _ = self._engine.static_io(offs, lens, B * T, slot)
-            if mix.is_cuda:
-                with torch.cuda.stream(compute):
-                    mix_buf.copy_(mix.reshape(-1), non_blocking=True)
-            else:
-                with torch.cuda.stream(h2d):
-                    mix_buf.copy_(mix.reshape(-1), non_blocking=True)
-                    up = torch.cuda.Event(); up.record(h2d)
-                compute.wait_event(up)
-            with torch.cuda.stream(compute):
-                est = torch.ops.clearconverse_b200.resep_separate_static(
-                    mix_buf, offs, lens, self._engine.id, _lib.PRECISIONS[self.precision],
-                    _lib.BATCH_MODES[self.batch_mode], slot).view(B, T, NUM_SPKS)
-            if device_out:
-                with torch.cuda.stream(compute):
-                    res = est.clone()
-                    fin = torch.cuda.Event(); fin.record(compute)
-                inflight.append((fin, res))
-                if len(inflight) >= depth:
-                    yield drain_one()
-                continue
-            done = torch.cuda.Event(); done.record(compute)
-            if out_buffers is not None:
-                host = out_buffers[i % len(out_buffers)]
-            else:
-                host = torch.empty(B, T, NUM_SPKS, dtype=torch.float32).pin_memory()
-            with torch.cuda.stream(d2h):
-                d2h.wait_event(done)
-                host.copy_(est, non_blocking=True)
-                down = torch.cuda.Event(); down.record(d2h)
-            inflight.append((down, host))
-            if len(inflight) >= depth:
+            while inflight:
                 yield drain_one()
-        while inflight:
-            yield drain_one()
+        finally:
+            # also on an abandoned generator or an exception: whatever the caller issues next on its stream is ordered
+            # after everything the lanes still have in flight (a device-side wait; the host does not block)
+            for st in self._pipe_streams:
+                caller.wait_stream(st)
 
     def separate_batch_debug(self, mix: torch.Tensor) -> tuple[torch.Tensor, dict]:
         """separate_batch + intermediates (encoder / block outputs) for per-kernel parity tests."""
@@ -572,14 +633,15 @@ class SepformerSeparation:
         return est.view(B, T, NUM_SPKS), dbg
 
     def separate_file(self, path: str, savedir: str | None = None) -> torch.Tensor:
-        """Upstream's convenience wrapper: load, mono-mix, resample to 8 kHz, separate, and
-        peak-normalise each source."""
-        import torchaudio
-        batch, fs = torchaudio.load(path)
-        batch = batch.mean(dim=0, keepdim=True).to(self.device)
+        """Upstream's convenience wrapper (speechbrain/inference/separation.py ``separate_file``): load, mono-mix and
+        resample to the model's 8 kHz when the file's rate differs, separate, and divide by the per-source peak.
+        Returns [1, T, n_spk] on ``self.device``.  The resampler is the device FIR pass (torchaudio's taps)."""
+        batch, fs = _load_audio(path)
+        batch = batch.to(self.device)
         if fs != SAMPLE_RATE:
+            batch = batch.mean(dim=0, keepdim=True)
             batch = self._engine.resample(batch.float().contiguous()[:, :, None], fs, SAMPLE_RATE)[:, :, 0]
-        est = self.separate_batch(batch.float())
+        est = self.separate_batch(batch.float().contiguous())
         return est / est.abs().max(dim=1, keepdim=True)[0]
 
     def launch_count(self) -> int:
@@ -599,4 +661,21 @@ class SepformerSeparation:
         return json.loads(buf.value.decode())
 
     def close(self):
-        self._engine.close()
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        # upstream's object releases its GPU memory when dropped; so does this one (device weights, workspaces,
+        # static I/O buffers, plans and CUDA graphs all hang off the engine)
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -9,7 +9,7 @@ import torch
 from clearconverse_b200 import SepformerSeparation
 from clearconverse_b200.synth import synth_batch
 from oracle.resepformer_oracle import OracleSepformerSeparation
-from test_gpu_parity import si_snr_db
+from clearconverse_b200.metrics import si_snr_db
 torch.set_num_threads(os.cpu_count())
 cases = [(2, 2000, 2), (1, 32000, 1), (3, 9000, 5), (8, 32000, 2)]
 out = {"note": "coupled batches, synthetic 8 kHz mixtures, random-init weights per seed; delta_db_well_conditioned = max |SI-SNR(est,mix) - "

@@ -6,7 +6,7 @@ import torch
 from clearconverse_b200 import SepformerSeparation
 from clearconverse_b200.synth import synth_batch
 from oracle.resepformer_oracle import OracleSepformerSeparation
-from test_gpu_parity import si_snr_db, si_snr_delta
+from clearconverse_b200.metrics import si_snr_db, si_snr_delta
 torch.set_num_threads(os.cpu_count())
 oracle = OracleSepformerSeparation(seed=0)
 sds = oracle.component_state_dicts()
@@ -19,14 +19,14 @@ for mode in ("bf16", "bf16x2", "mixed"):
     row = []
     for x, w in zip(cases, wants):
         g = sep.separate_batch(x).cpu()
-        row.append(f"{(g-w).abs().max():.1e} {si_snr_db(g.permute(0,2,1), w.permute(0,2,1)).min():.1f}dB d={si_snr_delta(g,w,x):.4f}")
+        row.append(f"{(g-w).abs().max():.1e} {si_snr_db(g.permute(0,2,1), w.permute(0,2,1)).min():.1f}dB d={si_snr_delta(g,w,x)[0]:.4f}")
     print(f"W16={mode:7s}", " | ".join(row), flush=True)
     sep.close()
 sep = SepformerSeparation(sds, device="cuda:0", precision="tf32")
 row = []
 for x, w in zip(cases, wants):
     g = sep.separate_batch(x).cpu()
-    row.append(f"{(g-w).abs().max():.1e} {si_snr_db(g.permute(0,2,1), w.permute(0,2,1)).min():.1f}dB d={si_snr_delta(g,w,x):.4f}")
+    row.append(f"{(g-w).abs().max():.1e} {si_snr_db(g.permute(0,2,1), w.permute(0,2,1)).min():.1f}dB d={si_snr_delta(g,w,x)[0]:.4f}")
 print("tf32(splitW)", " | ".join(row), flush=True)
 eng = sep._engine
 g = torch.Generator().manual_seed(3)

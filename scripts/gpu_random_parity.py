@@ -6,7 +6,7 @@ import torch
 from clearconverse_b200 import SepformerSeparation
 from clearconverse_b200.synth import synth_mixture
 from oracle.resepformer_oracle import OracleSepformerSeparation
-from test_gpu_parity import si_snr_db
+from clearconverse_b200.metrics import si_snr_db
 torch.set_num_threads(os.cpu_count())
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 oracle = OracleSepformerSeparation(seed=0)

@@ -11,7 +11,7 @@ import torch
 from oracle import functional_restatement as fr
 from oracle.resepformer_oracle import OracleSepformerSeparation
 from clearconverse_b200.synth import synth_batch
-from test_gpu_parity import si_snr_db, si_snr_delta
+from clearconverse_b200.metrics import si_snr_db, si_snr_delta
 
 torch.set_num_threads(os.cpu_count())
 D, H, DH = fr.D, fr.H, fr.DH
@@ -114,5 +114,5 @@ if __name__ == "__main__":
         row = []
         for x, wnt in zip(cases, wants):
             g = separate(x, sds, c)
-            row.append(f"{(g - wnt).abs().max():.1e} {si_snr_db(g.permute(0, 2, 1), wnt.permute(0, 2, 1)).min():.1f}dB d={si_snr_delta(g, wnt, x):.4f}")
+            row.append(f"{(g - wnt).abs().max():.1e} {si_snr_db(g.permute(0, 2, 1), wnt.permute(0, 2, 1)).min():.1f}dB d={si_snr_delta(g, wnt, x)[0]:.4f}")
         print(f"{name:32s}", " | ".join(row), flush=True)

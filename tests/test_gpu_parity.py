@@ -23,35 +23,22 @@ TOL_SPEC = 1e-3     # north_star: max-abs on fp32 waveforms
 TOL_BF16_MAXABS = 5e-2
 
 
-def si_snr_db(est: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
-    """Scale-invariant SNR in dB of est against ref along the last dim (zero-mean)."""
-    est = est.double() - est.double().mean(-1, keepdim=True)
-    ref = ref.double() - ref.double().mean(-1, keepdim=True)
-    proj = (est * ref).sum(-1, keepdim=True) * ref / (ref.pow(2).sum(-1, keepdim=True) + 1e-20)
-    noise = est - proj
-    return 10 * torch.log10(proj.pow(2).sum(-1) / (noise.pow(2).sum(-1) + 1e-20))
+from clearconverse_b200.metrics import (MAX_SI_SNR_DELTA_DB, MIN_EST_VS_EST_DB, MIN_REF_SI_SNR_DB, est_vs_est_db,  # noqa: E402
+                                        si_snr_db, si_snr_delta)
 
 
-MIN_REF_SI_SNR_DB = -20.0   # SI-SNR deltas are evaluated where the oracle's own SI-SNR is at least this
-MIN_EST_VS_EST_DB = 45.0    # weight-independent bf16 gate: error at least 45 dB below the oracle's estimate
-
-
-def si_snr_delta(est: torch.Tensor, oracle_est: torch.Tensor, mix: torch.Tensor, min_ref_db: float = MIN_REF_SI_SNR_DB) -> float:
-    """The bf16 acceptance metric.  With random-init weights SI-SNR against the true sources
-    sits near -38 dB where it is ill-conditioned, so the delta is taken
-    against a reference the estimates actually resemble: the mixture.  delta =
-    max over (item, speaker) of |SI-SNR(est, mix) - SI-SNR(oracle_est, mix)| in dB, over the pairs whose oracle
-    SI-SNR is >= min_ref_db.  A perturbation S dB below the estimate can move an SI-SNR of R dB by up to
-    20 log10(1 + 10^((|R| - S) / 20)): for R -> -inf (estimate orthogonal to the reference) any perturbation
-    moves it arbitrarily.  Measured with four weight seeds (scripts/gpu_accuracy.py): S = 49.8 ... 52.9 dB
-    everywhere; delta <= 0.043 dB for R >= -22 dB, 0.05-0.08 around -25 ... -31 dB, 0.15-1.3 dB below -45 dB.  A
-    trained separator sits at R >> 0 dB.  The pairs left out here are still held to MIN_EST_VS_EST_DB."""
-    a = si_snr_db(est.permute(0, 2, 1), mix[:, None, :])
-    b = si_snr_db(oracle_est.permute(0, 2, 1), mix[:, None, :])
-    ok = b >= min_ref_db
-    if not ok.any():
-        return 0.0
-    return (a - b).abs()[ok].max().item()
+def assert_bf16_gates(got, want, mix, unmasked=True, tag=""):
+    """The bf16 acceptance gates (definitions: clearconverse_b200/metrics.py).  Every (item, speaker) pair is held to
+    est-vs-oracle-est SI-SNR >= 45 dB.  The north star's SI-SNR delta <= 0.05 dB is held UNMASKED (every pair) where the
+    weights put every source at a usable SI-SNR against the mixture (weight seed 0: >= -20 dB; the filterbank set:
+    +5 ... +10 dB); with ``unmasked=False`` (weight seeds whose random filterbank leaves a speaker at -45 ... -73 dB)
+    over the pairs at >= -20 dB, and the gate FAILS if there is no such pair -- it cannot pass on an empty set."""
+    assert (got - want).abs().max().item() <= TOL_BF16_MAXABS, tag
+    assert est_vs_est_db(got, want) > MIN_EST_VS_EST_DB, tag
+    delta, pairs = si_snr_delta(got, want, mix, None if unmasked else MIN_REF_SI_SNR_DB)
+    assert pairs >= 1, f"{tag}: no (item, speaker) pair qualifies for the SI-SNR delta"
+    assert delta <= MAX_SI_SNR_DELTA_DB, f"{tag}: SI-SNR delta {delta:.4f} dB over {pairs} pairs"
+    return delta, pairs
 
 
 @pytest.fixture(scope="module")
@@ -262,9 +249,7 @@ def test_bf16_forward_within_spec(make_sep, oracle, B, T, seed):
     mix = synth_batch(B, T, seed)
     want = oracle.separate_batch(mix)
     got = sep.separate_batch(mix).cpu()
-    assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
-    assert si_snr_delta(got, want, mix) <= 0.05
-    assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB   # est vs fp32 est
+    assert_bf16_gates(got, want, mix, unmasked=True)
 
 
 @pytest.mark.parametrize("wseed", [1, 2, 3])
@@ -279,9 +264,7 @@ def test_bf16_other_weight_seeds(cuda_lib_built, wseed):
         for mix in (synth_batch(2, 2000, 2), synth_batch(3, 9000, 5)):
             want = oracle.separate_batch(mix)
             got = sep.separate_batch(mix).cpu()
-            assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
-            assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB
-            assert si_snr_delta(got, want, mix) <= 0.05
+            assert_bf16_gates(got, want, mix, unmasked=False, tag=f"weight seed {wseed}")
     finally:
         sep.close()
 
@@ -295,8 +278,14 @@ def test_config2_full_size_all_modes(make_sep, oracle):
         got = make_sep(prec, "coupled").separate_batch(mix).cpu()
         assert (got - want).abs().max().item() <= tol, prec
     got = make_sep("bf16", "coupled").separate_batch(mix).cpu()
-    assert si_snr_delta(got, want, mix) <= 0.05
-    assert si_snr_db(got.permute(0, 2, 1), want.permute(0, 2, 1)).min().item() > MIN_EST_VS_EST_DB
+    assert_bf16_gates(got, want, mix, unmasked=True, tag="config 2 coupled")
+    # the product-faithful semantics at the same size: per-item memory sequences == 16 oracle calls with B = 1
+    want_ind = torch.cat([oracle.separate_batch(mix[i:i + 1]) for i in range(16)])
+    for prec, tol in (("fp32", TOL_FP32), ("tf32", TOL_SPEC)):
+        got = make_sep(prec, "independent").separate_batch(mix).cpu()
+        assert (got - want_ind).abs().max().item() <= tol, prec
+    got = make_sep("bf16", "independent").separate_batch(mix).cpu()
+    assert_bf16_gates(got, want_ind, mix, unmasked=True, tag="config 2 independent")
 
 
 def test_config3_long_sequence_properties(make_sep, oracle):
@@ -312,6 +301,9 @@ def test_config3_long_sequence_properties(make_sep, oracle):
     assert (got.cpu() - want).abs().max().item() <= TOL_FP32
     tf = make_sep("tf32", "coupled").separate_batch(mix).cpu()
     assert (tf - want).abs().max().item() <= TOL_SPEC
+    # the bf16 budget "must be re-checked at 60 s" (400 chunks through the memory transformer)
+    bf = make_sep("bf16", "coupled").separate_batch(mix).cpu()
+    assert_bf16_gates(bf, want, mix, unmasked=True, tag="config 3")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -376,6 +368,7 @@ def test_bf16_ragged_independent_segments(make_sep, oracle):
         assert (got - want).abs().max().item() <= TOL_BF16_MAXABS
         if s.numel() >= 1000:
             assert si_snr_db(got.T[None], want.T[None]).min().item() > MIN_EST_VS_EST_DB
+            assert_bf16_gates(got[None], want[None], s[None], unmasked=True, tag=f"segment of {s.numel()}")
 
 
 def test_sliced_intra_blocks_match_unsliced(sds, cuda_lib_built):
@@ -569,3 +562,196 @@ def test_ragged_batches_through_the_pipelined_driver(make_sep):
     res_a, n_a = sharding.separate_sharded(segs, sep.separate_segments, 0, 1, max_chunks_per_batch=40)
     res_b, n_b = sharding.separate_sharded(segs, sep.separate_segments, 0, 1, max_chunks_per_batch=40, pipeline=sep.separate_stream)
     assert n_a == n_b == sum(lens) and all(torch.equal(a, b) for a, b in zip(res_a, res_b))
+
+
+# ------------------------------------------------------------------ round 2: hardened parity ("next round" item 1)
+def _oracle_from(sds):
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    m = OracleSepformerSeparation(seed=None, distinct_blocks=False)
+    for k in ("encoder", "masknet", "decoder"):
+        m.mods[k].load_state_dict(sds[k])
+    return m
+
+
+@pytest.mark.parametrize("wseed", [0, 3])
+def test_bf16_unmasked_si_snr_delta_on_filterbank_weights(cuda_lib_built, wseed):
+    """The north star's bf16 tolerance on a WELL-CONDITIONED weight set, with no mask: the random masknet of the given
+    seed (seed 3 is the one whose random filterbank leaves a speaker at -73 dB) between a reconstructing analysis /
+    synthesis filterbank (weights.filterbank_init_state_dicts).  Every separated source then sits at SI-SNR(est, mix)
+    of a few dB -- asserted -- and |SI-SNR(bf16) - SI-SNR(oracle)| <= 0.05 dB must hold for EVERY (item, speaker)."""
+    from clearconverse_b200 import SepformerSeparation, weights
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    base = OracleSepformerSeparation(seed=wseed).component_state_dicts()
+    sds_fb = weights.filterbank_init_state_dicts(base=base)
+    oracle_fb = _oracle_from(sds_fb)
+    for mode in ("coupled", "independent"):
+        sep = SepformerSeparation(sds_fb, device="cuda:0", precision="bf16", batch_mode=mode)
+        try:
+            for mix in (synth_batch(2, 16000, 2), synth_batch(3, 9000, 5), synth_batch(1, 32000, 1)):
+                want = oracle_fb.separate_batch(mix) if mode == "coupled" else \
+                    torch.cat([oracle_fb.separate_batch(mix[i:i + 1]) for i in range(mix.shape[0])])
+                ref_snr = si_snr_db(want.permute(0, 2, 1), mix[:, None, :])
+                assert ref_snr.min().item() > 0.0 and ref_snr.max().item() < 25.0, ref_snr    # well-conditioned, both ways
+                got = sep.separate_batch(mix).cpu()
+                delta, pairs = assert_bf16_gates(got, want, mix, unmasked=True, tag=f"filterbank weights, seed {wseed}, {mode}")
+                assert pairs == 2 * mix.shape[0]
+        finally:
+            sep.close()
+
+
+def test_from_hparams_end_to_end_like_api_py(tmp_path, oracle, sds):
+    """The drop-in's constructor and weight path exactly as /root/reference/back/api.py uses them:
+    ``SepformerSeparation.from_hparams(source=..., savedir=..., run_opts={"device": ...})`` (:713-717) over a directory
+    holding encoder.ckpt / masknet.ckpt / decoder.ckpt (:729; masknet.ckpt carries the pos_enc.pe buffers upstream
+    saves), then the ``load_state_dict({...}, strict=False)`` call of :738-745 (a silent no-op upstream, must not
+    raise), then ``separate_batch`` on a [1,T] slice (:1074-1077) -- against the oracle loaded from the same files."""
+    from clearconverse_b200 import SepformerSeparation
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    src = OracleSepformerSeparation(seed=5)                      # not the module-wide seed: the files decide the result
+    torch.save(src.mods["encoder"].state_dict(), tmp_path / "encoder.ckpt")
+    from clearconverse_b200.weights import positional_table
+    mk = dict(src.mods["masknet"].state_dict())
+    for blk in ("model.seg_model.0.", "model.seg_model.1.", "model.mem_model.0."):   # upstream saves this buffer per block
+        mk[blk + "pos_enc.pe"] = positional_table(2000)[None]                         # ([1,100000,128] there: 51 MB each)
+    torch.save(mk, tmp_path / "masknet.ckpt")
+    torch.save(src.mods["decoder"].state_dict(), tmp_path / "decoder.ckpt")
+    (tmp_path / "hyperparams.yaml").write_text("# speechbrain/resepformer-wsj02mix\nsample_rate: 8000\nnum_spks: 2\n")
+    assert any(k.endswith("pos_enc.pe") for k in torch.load(tmp_path / "masknet.ckpt", weights_only=True))
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")       # api.py:587
+    separator = SepformerSeparation.from_hparams(source="speechbrain/resepformer-wsj02mix", savedir=str(tmp_path),
+                                                 run_opts={"device": device})
+    try:
+        # api.py:738-745
+        masknet_state_dict = torch.load(tmp_path / "masknet.ckpt", map_location=device)
+        encoder_state_dict = torch.load(tmp_path / "encoder.ckpt", map_location=device)
+        decoder_state_dict = torch.load(tmp_path / "decoder.ckpt", map_location=device)
+        state_dict = {"masknet": masknet_state_dict, "encoder": encoder_state_dict, "decoder": decoder_state_dict}
+        separator.load_state_dict(state_dict, strict=False)
+        # api.py:1074-1081
+        audio = synth_mixture(20000, 77)[0].to(device)[None]
+        subsegment = audio[:, 3000:15000]
+        separated = separator.separate_batch(subsegment)
+        assert separated.shape == (1, 12000, 2) and separated.shape[-1] == 2 and separated.is_cuda
+        twin = OracleSepformerSeparation(seed=None, distinct_blocks=False)      # the oracle, loaded from the same files
+        for name in ("encoder", "masknet", "decoder"):
+            sd = torch.load(tmp_path / f"{name}.ckpt", weights_only=True)
+            twin.mods[name].load_state_dict({k: v for k, v in sd.items() if not k.endswith("pos_enc.pe")})
+        want = twin.separate_batch(subsegment.cpu())
+        assert separator.precision == "tf32"                                     # the package default: the 1e-3 contract
+        assert (separated.cpu() - want).abs().max().item() <= TOL_SPEC
+        assert (separated.cpu() - oracle.separate_batch(subsegment.cpu())).abs().max().item() > 1e-2   # really these files' weights
+        assert separator.hparams.num_spks == 2 and separator.hparams.sample_rate == 8000
+        with pytest.raises(FileNotFoundError):
+            SepformerSeparation.from_hparams(source="speechbrain/resepformer-wsj02mix", savedir=str(tmp_path / "none"),
+                                             run_opts={"device": device})
+    finally:
+        separator.close()
+
+
+def test_separate_file_like_upstream(tmp_path, make_sep):
+    """``separate_file`` (upstream's convenience wrapper): a 16 kHz stereo PCM file is mono-mixed, resampled to the
+    model's 8 kHz on the device, separated and peak-normalised; an 8 kHz mono file goes straight through."""
+    import numpy as np
+    from scipy.io import wavfile
+    import torchaudio.functional as AF
+    sep = make_sep("fp32", "coupled")
+    x8 = synth_mixture(12000, 5)[0]
+    pcm = (x8 * 32767).round().clamp(-32768, 32767).to(torch.int16)
+    wavfile.write(tmp_path / "mono8k.wav", 8000, pcm.numpy())
+    got = sep.separate_file(str(tmp_path / "mono8k.wav"))
+    est = sep.separate_batch((pcm.float() / 32768.0)[None])
+    want = est / est.abs().max(dim=1, keepdim=True)[0]
+    assert got.shape == (1, 12000, 2) and (got - want).abs().max().item() <= 1e-6
+    assert abs(got.abs().amax(dim=1).max().item() - 1.0) < 1e-6
+    x16 = AF.resample(x8[None], 8000, 16000)[0]
+    stereo = torch.stack([x16, 0.5 * x16], dim=1)                                   # [T, 2]
+    wavfile.write(tmp_path / "stereo16k.wav", 16000, stereo.numpy().astype(np.float32))
+    got16 = sep.separate_file(str(tmp_path / "stereo16k.wav"))
+    mono8 = AF.resample(stereo.mean(dim=1)[None], 16000, 8000)
+    est = sep.separate_batch(mono8)
+    want16 = est / est.abs().max(dim=1, keepdim=True)[0]
+    assert got16.shape == want16.shape and (got16 - want16).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tf32", 2e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("block,layer,n_seq,seq_len", [(0, 0, 5, 150), (1, 7, 3, 150), (2, 3, 1, 40), (2, 0, 1, 432)])
+def test_layer_entry_point_matches_oracle_layer(make_sep, oracle, prec, tol, block, layer, n_seq, seq_len):
+    """``resep_layer_fwd`` (per-kernel entry point of the C ABI): one pre-norm TransformerEncoderLayer on [n_seq,
+    seq_len, 128] against the same layer of the oracle's module tree (intra chunk shapes and memory-sequence shapes)."""
+    sep = make_sep(prec, "coupled")
+    eng = sep._engine
+    blk = oracle.mods["masknet"].model.seg_model[block] if block < 2 else oracle.mods["masknet"].model.mem_model[0]
+    lyr = blk.mdl.layers[layer]
+    g = torch.Generator().manual_seed(100 * block + layer)
+    x = torch.randn(n_seq, seq_len, 128, generator=g)
+    with torch.no_grad():
+        want = lyr(x)[0]                                       # (output, attention weights)
+    rows = n_seq * seq_len
+    d_x = x.reshape(rows, 128).cuda().contiguous()
+    lens = (C.c_int64 * 1)(16 + 8 * (rows + 300))                 # a workspace sized for at least `rows` token rows
+    need = C.c_size_t()
+    assert eng.lib.resep_workspace_bytes(eng.handle, 1, lens, 0, C.byref(need)) == 0
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    rc = eng.lib.resep_layer_fwd(eng.handle, block, layer, d_x.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(),
+                                 {"fp32": 0, "tf32": 1, "bf16": 2}[prec], C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, eng.lib.resep_last_error(eng.handle)
+    torch.cuda.synchronize()
+    got = d_x.cpu().view(n_seq, seq_len, 128)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+
+def test_separator_releases_gpu_memory_when_dropped(sds, cuda_lib_built):
+    """Upstream's object frees its memory when it goes out of scope; so must the drop-in (the engine
+    registry used to hold a strong reference, leaking weights, workspaces, static I/O buffers and graphs)."""
+    import gc
+    from clearconverse_b200 import SepformerSeparation, separation
+    torch.cuda.synchronize()
+    gc.collect(); torch.cuda.empty_cache()
+    free0, _ = torch.cuda.mem_get_info()
+    n0 = len(separation._ENGINES)
+    for _ in range(3):
+        sep = SepformerSeparation(sds, device="cuda:0", precision="bf16", batch_mode="coupled")
+        sep.separate_batch(synth_batch(8, 32000, 1))
+        assert len(separation._ENGINES) == n0 + 1
+        del sep
+        gc.collect()
+        assert len(separation._ENGINES) == n0
+    with SepformerSeparation(sds, device="cuda:0", precision="fp32") as sep:
+        sep.separate_batch(synth_batch(1, 4000, 1))
+    torch.cuda.synchronize()
+    gc.collect(); torch.cuda.empty_cache()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"{(free0 - free1) >> 20} MiB still held after dropping four separators"
+
+
+def test_blocking_call_inside_a_half_consumed_stream(make_sep):
+    """separate_batch while a separate_stream generator is partly consumed (same batch shape), and after a
+    generator has been abandoned: the blocking path owns its workspace lane and I/O slot, so nothing races."""
+    sep = make_sep("bf16", "coupled")
+    batches = [synth_batch(4, 16000, 600 + i).pin_memory() for i in range(6)]
+    want = [sep.separate_batch(b).cpu() for b in batches]
+    gen = sep.separate_stream(iter(batches), depth=2)
+    got0 = next(gen).clone()
+    mid = sep.separate_batch(batches[3]).cpu()                     # same shape as what the lanes are running right now
+    got1 = next(gen).clone()
+    gen.close()                                                    # abandoned with batches in flight
+    after = sep.separate_batch(batches[5]).cpu()
+    assert torch.equal(got0, want[0]) and torch.equal(got1, want[1])
+    assert torch.equal(mid, want[3]) and torch.equal(after, want[5])
+    outs = [o.clone() for o in sep.separate_stream(iter(batches), depth=2)]
+    assert all(torch.equal(o, w) for o, w in zip(outs, want))
+
+
+def test_stream_of_distinct_lengths_like_the_product(make_sep, oracle):
+    """The reference's real call pattern (api.py:1073-1077): B = 1, a different length on every call.  80 distinct
+    lengths overflow the plan table (64) and the static-I/O table (24): eviction must neither corrupt results nor
+    leak; spot-check against the oracle and against a repeat of the first lengths."""
+    sep = make_sep("fp32", "independent")
+    lens = [2400 + 37 * i for i in range(80)]
+    segs = [synth_mixture(n, 900 + i)[0][None] for i, n in enumerate(lens)]
+    outs = [sep.separate_batch(s).cpu() for s in segs]
+    for i in (0, 41, 79):
+        assert (outs[i] - oracle.separate_batch(segs[i])).abs().max().item() < TOL_FP32
+    for i in range(0, 80, 9):
+        assert torch.equal(sep.separate_batch(segs[i]).cpu(), outs[i])
