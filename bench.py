@@ -15,6 +15,14 @@ goes through the public Python API with pinned HOST buffers, H2D and D2H inside 
 region.  ``roofline`` is the dominant kernel of the step (CUDA-event timing per kernel on the
 launch stream, taken in a separate pass); ``cpu_baseline`` is the oracle (the only runnable
 form of the reference's CPU path: speechbrain is not installable here) on the host cores.
+
+Side blocks of the same line (none of them changes ``value``):
+  ``sustained``   the same step repeated for >= 3 s with clocks and power sampled throughout;
+  ``meeting``     BASELINE configs[3]: the overlap segments of a synthetic 1-hour meeting (720 s, 0.5-30 s,
+                  log-uniform, seed 4) through ``sharding.separate_sharded`` -- planning, H2D, kernels, D2H and the
+                  host gather inside the timed region; the SAME segment list at every N (strong scaling);
+  ``long_split``  (N > 1) one 60 s recording split by chunks across the ranks: bit-identity flag and time;
+  ``latency``     one B = 1 call of 4 s (the reference's call pattern), repeated shape vs. a stream of distinct lengths.
 """
 from __future__ import annotations
 
@@ -80,7 +88,7 @@ def kernel_work(name: str, batch: int, t: int):
         return "tensor", rows * (32_768 + 524_288)
     if name.startswith("k_qkv"):                       # fused LN1 + in-projection: 512 B in + 768 B out per row, HBM-bound
         return "hbm", rows * (512 + 768)
-    if name.startswith("k_attention_bf16_tma"):        # every intra chunk (TMA-fed per-(chunk, head) kernel)
+    if name.startswith("k_attention_bf16_tma") or name.startswith("k_attn_tc"):   # every intra chunk
         return "tensor", att_intra
     if name.startswith("k_attention_bf16_short"):      # sequences <= 160 rows (every intra chunk)
         return "tensor", att_intra + sum(8 * 4 * n * n * 128 for n in mem_seqs if n <= 160)
@@ -104,7 +112,7 @@ class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.power, self.reasons, self.max_mhz = [], [], set(), None
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -127,6 +135,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1e3)
+                except Exception:
+                    pass
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
                 except Exception:
@@ -151,7 +163,15 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": (max(self.power) if self.power else None)}
+
+
+def bench_config(world: int) -> dict:
+    """The ``config`` object of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "seconds_per_item": SECONDS, "sample_rate": SAMPLE_RATE,
+            "batch_mode": "coupled", "parallelism": f"replicated x{world}, no collective",
+            "l2": "inputs rotated over 64 device-resident batches (128 MiB > the 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
@@ -208,7 +228,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": BATCH, "seconds_per_item": SECONDS, "sample_rate": SAMPLE_RATE},
+        "config": bench_config(int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -969,7 +969,14 @@ static int launch_attention_tf32mode(ResepHandle* h, const float* qkv, float* ct
 }
 
 static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int n_seq, int seq_len, const int* seq_off,
-                                 const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st) {
+                                 const int* tile_seq, const int* tile_q0, int n_tiles128, int max_len, cudaStream_t st, bool intra) {
+  // The intra blocks (every sequence is a 150-row chunk) run on tcgen05.  The memory transformer's sequences never do,
+  // whatever their length: which of ITS kernels a sequence gets depends on the batch composition, and those are
+  // bit-identical to one another by construction -- the tcgen05 kernel's arithmetic is not.
+  static const bool use_tc = attn_tc_default() ? !(getenv("RESEP_ATTN_TC") && getenv("RESEP_ATTN_TC")[0] == '0')
+                                               : (getenv("RESEP_ATTN_TC") && getenv("RESEP_ATTN_TC")[0] == '1');
+  if (intra && use_tc && tile_seq == nullptr && seq_len == CHUNK && (int64_t)n_seq * seq_len < 2000000000LL)
+    return launch_attn_tc(h, qkv, ctx, n_seq, st);
   const int longest = tile_seq == nullptr ? seq_len : max_len;
   ProfScope prof_scope(h, longest <= 160 ? (tile_seq == nullptr ? "k_attention_bf16_tma" : "k_attention_bf16_short") : longest <= 448 ? "k_attention_bf16_mid" : "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
@@ -1071,7 +1078,7 @@ int tc_linear_test(ResepHandle* h, const float* A, const float* W, const float* 
 //   tf32 mode: fp32 buffers holding tf32-rounded values; attention uses the fp32 kernel
 int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
                  const int* tile_seq, const int* tile_q0, int n_tiles, int max_seq_len, float* y, float* qkv, float* ctx, float* hid,
-                 int precision, cudaStream_t st) {
+                 int precision, cudaStream_t st, bool intra) {
   int rc;
   if (precision == RESEP_PREC_BF16) {
     bf16 *yb = reinterpret_cast<bf16*>(y), *qb = reinterpret_cast<bf16*>(qkv), *cb = reinterpret_cast<bf16*>(ctx),
@@ -1084,7 +1091,7 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
       if ((rc = launch_layernorm<bf16>(h, o, lw.norm1_w, lw.norm1_b, yb, rows, st))) return rc;
       if ((rc = gemm_bf16<EPI_STORE_BF16>(h, h->w16_mode, yb, lw.in_w_bf, lw.in_w_bl, lw.in_b_hi, qb, rows, 3 * D, D, false, st))) return rc;
     }
-    if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st))) return rc;
+    if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st, intra))) return rc;
     static const bool post2 = !(getenv("RESEP_POST2") && getenv("RESEP_POST2")[0] == '0');
     if (fused) return post2 ? launch_post2_tc(h, lw, cb, o, rows, st) : launch_post_tc(h, lw, cb, o, rows, st);   // out-proj + LN2 + FFN in one kernel
     if ((rc = gemm_bf16<EPI_RESID_F32>(h, h->w16_mode, cb, lw.out_w_bf, lw.out_w_bl, lw.out_b, o, rows, D, D, false, st))) return rc;

@@ -108,6 +108,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // [61,64) layout: SWIZZLE_128B
   return d;
 }
+// Shared-memory matrix descriptor, MN-major operand (rows of the tile run along K, the 128-byte row holds up to 64
+// MN elements), 128-byte swizzle: 8-row groups along K are SBO = 1024 B apart; LBO (stride between 64-element MN
+// blocks) is unused for N <= 64.  Verified on a B200 with a 32-byte slice inside the swizzled row (start address
+// advanced by the slice's byte offset): scripts/microbench/attn_probe.cu, profiles/r2_attn_probe.txt.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t UMMA_IDESC_B_MN_MAJOR = 1u << 16;   // instruction-descriptor bit: B operand is MN-major
 enum : uint32_t { UMMA_F16 = 0, UMMA_BF16 = 1, UMMA_TF32 = 2 };
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_format, uint32_t b_format, int M, int N) {
@@ -250,6 +264,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

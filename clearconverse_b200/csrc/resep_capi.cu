@@ -368,6 +368,7 @@ struct SeqDesc {          // the sequences one transformer block runs over
   const int* tile_q0;
   int n_tiles;
   int max_len;            // longest sequence
+  bool intra = false;     // the sequences are the 150-row chunks of an intra block (not a memory sequence that happens to be 150 long)
 };
 
 static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc& sd, const Workspace& ws, int precision,
@@ -385,7 +386,7 @@ static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc
     return RESEP_OK;
   }
   return tc_run_layer(h, lw, o, sd.rows, sd.n_seq, sd.seq_len, sd.seq_off, sd.tile_seq, sd.tile_q0, sd.n_tiles, sd.max_len, ws.y,
-                      ws.qkv, ws.ctx, ws.hid, precision, st);
+                      ws.qkv, ws.ctx, ws.hid, precision, st, sd.intra);
 }
 
 static int run_block(ResepHandle* h, int blk, const float* xprev, const float* hc, float* xin, float* o, float* out,
@@ -520,7 +521,7 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
                        bf16* prelu_out_) -> int {
     for (int64_t c0 = 0; c0 < p->n_chunks; c0 += slice) {
       const int64_t nc = std::min<int64_t>(slice, p->n_chunks - c0), r0 = c0 * CHUNK * D;
-      SeqDesc sl{nc * CHUNK, (int)nc, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK};
+      SeqDesc sl{nc * CHUNK, (int)nc, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK, true};
       int rc2 = run_block(h, blk, xprev + r0, hc ? hc + c0 * D : nullptr, xin + r0, ws.o, out + r0,
                           seq_mean ? seq_mean + c0 * D : nullptr, sl, ws, precision, st, prelu_out_ ? prelu_out_ + r0 : nullptr);
       if (rc2) return rc2;
@@ -651,6 +652,13 @@ extern "C" int resep_debug_trace(long long* out) {
   if (!resep::g_post_trace) return -1;
   cudaDeviceSynchronize();
   return cudaMemcpy(out, resep::g_post_trace, 1536 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+
+// development aid (not in the public header): the k_attn_tc clock trace of CTA 0, [2 roles][512] (tag, clock) pairs
+extern "C" int resep_debug_attn_trace(long long* out) {
+  if (!resep::g_attn_trace) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, resep::g_attn_trace, 2048 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
 
 int resep_profile(ResepHandle* h, int enable) {
@@ -805,7 +813,7 @@ int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, i
   int rc;
   if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
   const int blk = block == 2 ? 2 : block;
-  SeqDesc sd{rows, n_seq, seq_len, nullptr, nullptr, nullptr, nullptr, 0, seq_len};
+  SeqDesc sd{rows, n_seq, seq_len, nullptr, nullptr, nullptr, nullptr, 0, seq_len, block < 2 && seq_len == CHUNK};
   return run_layer(h, h->w.blk[blk].layers[layer], x, sd, ws, precision, static_cast<cudaStream_t>(stream));
 }
 

@@ -9,6 +9,7 @@ algorithmic FLOPs, and results are gathered on the host into segment order.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 KSZ, STRIDE, CHUNK = 16, 8, 150
@@ -97,8 +98,71 @@ def plan_shards(lens: list[int], world_size: int, max_chunks_per_batch: int = 20
     return batches, assign_to_ranks(batches, world_size)
 
 
+class SharedResults:
+    """The host-side gather of the sharded path without pickling: ONE result buffer [sum_i T_i, n_spk] float32 in POSIX
+    shared memory (``/dev/shm``), mapped by every rank of the box and page-locked (``cudaHostRegister``), so each rank's
+    device->host copies land directly at their segments' final offsets and rank 0 reads all results in place after a
+    barrier.  The barrier is a counter array in the same mapping (no collective, no process group needed).
+
+    Rank 0 creates the buffer; the other ranks attach (the caller makes sure creation happens first, e.g. by
+    constructing it before / after a ``dist.barrier()`` or by creating it in the parent).  ``view(i)`` is segment i's
+    [T_i, n_spk] slice of the mapping: copy it if it has to outlive ``close()``."""
+
+    HEADER = 4096                                     # bytes reserved for the barrier counters (int64 per rank)
+
+    def __init__(self, lens: list[int], name: str, rank: int, world_size: int, n_spk: int = 2, pin: bool = True):
+        import numpy as np
+        import torch
+        self.lens, self.rank, self.world, self.n_spk = [int(t) for t in lens], rank, world_size, n_spk
+        self.offs = [0]
+        for t in self.lens:
+            self.offs.append(self.offs[-1] + t)
+        self.path = os.path.join("/dev/shm", name)
+        self.nbytes = self.HEADER + self.offs[-1] * n_spk * 4
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        self._map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+        self._ctr = self._map[:self.HEADER].view(np.int64)
+        self.data = torch.from_numpy(self._map[self.HEADER:].view(np.float32)).view(self.offs[-1], n_spk)
+        self._epoch = 0
+        self._pinned = False
+        if pin and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.data.data_ptr(), self.data.numel() * 4, 0)
+            self._pinned = int(rc) == 0
+
+    def view(self, i: int):
+        return self.data[self.offs[i]:self.offs[i + 1]]
+
+    def barrier(self, timeout_s: float = 120.0):
+        """All ranks of the box have written their results (spins on the shared counters)."""
+        import time
+        self._epoch += 1
+        self._ctr[self.rank] = self._epoch
+        t0 = time.perf_counter()
+        while True:
+            if all(int(self._ctr[r]) >= self._epoch for r in range(self.world)):
+                return
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError("SharedResults.barrier: a rank did not arrive")
+
+    def close(self):
+        import torch
+        if self._pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.data.data_ptr())
+            self._pinned = False
+        self.data = None
+        self._ctr = None
+        self._map = None
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def separate_sharded(segments, separate_fn, rank: int = 0, world_size: int = 1, group=None,
-                     max_chunks_per_batch: int = 2048, gather: bool = True, pipeline=None):
+                     max_chunks_per_batch: int = 2048, gather: bool = True, pipeline=None, shared: "SharedResults | None" = None):
     """Run this rank's share of ``segments`` (list of 1-D float32 tensors) through
     ``separate_fn(list_of_segments) -> list of [T_i, n_spk] tensors`` and, if ``gather``,
     collect all results on rank 0 in the original order (host-side gather, no NCCL).
@@ -107,24 +171,41 @@ def separate_sharded(segments, separate_fn, rank: int = 0, world_size: int = 1, 
     (``SepformerSeparation.separate_stream``): this rank's batches then run through it, two in flight, instead of
     one ``separate_fn`` call after the other.
 
+    ``shared`` (optional, a ``SharedResults`` built over the same segment lengths on every rank): results are copied
+    device->host straight into the shared, page-locked buffer and the gather is a barrier -- rank 0 gets views of the
+    buffer, the other ranks None.  Without it the gather pickles the tensors through ``dist.gather_object``.
+
     Returns (results or None on non-zero ranks, audio samples this rank processed)."""
     lens = [int(s.numel()) for s in segments]
     batches, per_rank = plan_shards(lens, world_size, max_chunks_per_batch)
     mine: dict[int, object] = {}
     samples = 0
+
+    def take(idx, outs):
+        nonlocal samples
+        for i, o in zip(idx, outs):
+            if shared is not None:
+                shared.view(i).copy_(o, non_blocking=True)      # D2H to the segment's final place
+            else:
+                mine[i] = o
+            samples += lens[i]
+
     if pipeline is not None:
         mine_batches = [batches[b].indices for b in per_rank[rank]]
         for idx, outs in zip(mine_batches, pipeline([segments[i] for i in idx] for idx in mine_batches)):
-            for i, o in zip(idx, outs):
-                mine[i] = o
-                samples += lens[i]
+            take(idx, outs)
     else:
         for b in per_rank[rank]:
             idx = batches[b].indices
-            outs = separate_fn([segments[i] for i in idx])
-            for i, o in zip(idx, outs):
-                mine[i] = o
-                samples += lens[i]
+            take(idx, separate_fn([segments[i] for i in idx]))
+    if shared is not None:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()           # this rank's copies have landed
+        if not gather:
+            return None, samples
+        shared.barrier()
+        return ([shared.view(i) for i in range(len(segments))] if rank == 0 else None), samples
     if not gather:
         return mine, samples
     if world_size == 1:

@@ -495,8 +495,8 @@ def test_bf16_fallback_paths_agree_with_the_default(cuda_lib_built):
         "sep = SepformerSeparation(weights.random_init_state_dicts(0), device='cuda:0', precision='bf16', batch_mode='coupled')\n"
         "torch.save(sep.separate_batch(synth.synth_batch(2, 6000, 3)).cpu(), sys.argv[1])\n"
         % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    knobs = ["", "RESEP_QKV2=0", "RESEP_POST2=0", "RESEP_FUSED=0", "RESEP_ATTN_TMA=0", "RESEP_W16=bf16x2", "RESEP_PDL=0",
-             "RESEP_GRAPH=0", "RESEP_MASKDEC=0"]
+    knobs = ["", "RESEP_QKV2=0", "RESEP_POST2=0", "RESEP_FUSED=0", "RESEP_ATTN_TC=0", "RESEP_ATTN_POLY=0", "RESEP_ATTN_TMA=0",
+             "RESEP_W16=bf16x2", "RESEP_PDL=0", "RESEP_GRAPH=0", "RESEP_MASKDEC=0"]
     outs = {}
     with tempfile.TemporaryDirectory() as d:
         for k in knobs:
@@ -755,3 +755,43 @@ def test_stream_of_distinct_lengths_like_the_product(make_sep, oracle):
         assert (outs[i] - oracle.separate_batch(segs[i])).abs().max().item() < TOL_FP32
     for i in range(0, 80, 9):
         assert torch.equal(sep.separate_batch(segs[i]).cpu(), outs[i])
+
+
+def test_tcgen05_attention_against_the_mma_sync_kernel(cuda_lib_built):
+    """k_attn_tc (intra-chunk attention on tcgen05 / TMEM) against its mma.sync predecessor (RESEP_ATTN_TC=0, subprocess)
+    on the same bf16 q | k | v, through ``resep_layer_fwd``: ordinary weights (Cauchy-Schwarz stabiliser, half of the
+    exponentials on the polynomial path) and in-projection weights scaled by 5 (scores far outside the stabiliser's
+    range: every warp takes the exact-row-maximum path, softmax nearly one-hot).  Chunk counts cover every
+    heads-per-item split (1, 2, 4, 8 heads per CTA) and more chunks than SMs."""
+    import subprocess, sys, tempfile
+    code = (
+        "import sys, ctypes as C, torch; sys.path.insert(0, %r)\n"
+        "from clearconverse_b200 import SepformerSeparation, weights\n"
+        "sds = weights.random_init_state_dicts(3)\n"
+        "scale = float(sys.argv[2])\n"
+        "for k in list(sds['masknet']):\n"
+        "    if 'in_proj' in k: sds['masknet'][k] = sds['masknet'][k] * scale\n"
+        "sep = SepformerSeparation(sds, device='cuda:0', precision='bf16')\n"
+        "eng = sep._engine; outs = {}\n"
+        "for n_seq in (1, 5, 20, 50, 160, 433):\n"
+        "    g = torch.Generator().manual_seed(n_seq)\n"
+        "    x = torch.randn(n_seq * 150, 128, generator=g).cuda()\n"
+        "    lens = (C.c_int64 * 1)(16 + 8 * (n_seq * 150 + 300)); need = C.c_size_t()\n"
+        "    assert eng.lib.resep_workspace_bytes(eng.handle, 1, lens, 2, C.byref(need)) == 0\n"
+        "    ws = torch.empty(need.value, dtype=torch.uint8, device='cuda')\n"
+        "    rc = eng.lib.resep_layer_fwd(eng.handle, 1, 2, x.data_ptr(), n_seq, 150, ws.data_ptr(), ws.numel(), 2, C.c_void_p(torch.cuda.current_stream().cuda_stream))\n"
+        "    assert rc == 0, eng.lib.resep_last_error(eng.handle)\n"
+        "    torch.cuda.synchronize(); outs[n_seq] = x.cpu()\n"
+        "torch.save(outs, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    with tempfile.TemporaryDirectory() as d:
+        for scale, min_db in (("1.0", 45.0), ("5.0", 25.0)):
+            res = {}
+            for flag in ("1", "0"):
+                path = os.path.join(d, f"a_{scale}_{flag}.pt")
+                subprocess.run([sys.executable, "-c", code, path, scale], check=True, env=dict(os.environ, RESEP_ATTN_TC=flag))
+                res[flag] = torch.load(path)
+            for n_seq, got in res["1"].items():
+                want = res["0"][n_seq]
+                assert torch.isfinite(got).all(), (scale, n_seq)
+                err = (got - want).double().pow(2).sum().sqrt() / want.double().pow(2).sum().sqrt()
+                assert -20 * torch.log10(err).item() > min_db, (scale, n_seq, err.item())

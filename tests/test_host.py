@@ -130,11 +130,27 @@ def _gloo_worker(rank, world, port, q):
     res, samples = sharding.separate_sharded(segs, fake_separate, rank, world)
     total = torch.tensor([samples])
     dist.all_reduce(total)
+    ok = rank != 0 or all(torch.equal(r, torch.stack([s + 1, s - 1], dim=-1)) for r, s in zip(res, segs))
+    assert rank == 0 or res is None
+    # the same through the shared-memory gather (no pickling: every rank writes its results in place, rank 0 reads)
+    name = f"resep_test_{port}"
     if rank == 0:
-        ok = all(torch.equal(r, torch.stack([s + 1, s - 1], dim=-1)) for r, s in zip(res, segs))
+        shared = sharding.SharedResults([s.numel() for s in segs], name, rank, world)
+    dist.barrier()
+    if rank != 0:
+        shared = sharding.SharedResults([s.numel() for s in segs], name, rank, world)
+    for rep in range(3):                                        # the barrier counters are reusable
+        res2, samples2 = sharding.separate_sharded(segs, fake_separate, rank, world, shared=shared)
+        assert samples2 == samples
+        if rank == 0:
+            ok = ok and all(torch.equal(r, torch.stack([s + 1, s - 1], dim=-1)) for r, s in zip(res2, segs))
+        else:
+            assert res2 is None
+        dist.barrier()
+    shared.close()
+    if rank == 0:
+        ok = ok and not os.path.exists(os.path.join("/dev/shm", name))
         q.put((ok, int(total.item()), sum(s.numel() for s in segs)))
-    else:
-        assert res is None
     dist.destroy_process_group()
 
 
@@ -279,3 +295,82 @@ def test_filterbank_weight_set_reconstructs_and_is_well_conditioned(oracle, sds)
     est = m.separate_batch(x)
     r = metrics.si_snr_db(est.permute(0, 2, 1), x[:, None, :])
     assert r.min().item() > 0.0 and r.max().item() < 25.0
+
+
+# ------------------------------------------------------------------ the re-segmentation feeder
+def test_find_overlaps_sweep_matches_bruteforce():
+    """find_segment_overlaps (api.py:323-343): for two speakers every maximal stretch where both talk, and nothing
+    else; threshold filter of _detect_overlap_regions (api.py:881-891)."""
+    from clearconverse_b200 import feeder
+    segs = [(0.0, 5.0, "A"), (4.0, 9.0, "B"), (8.7, 12.0, "A"), (12.0, 14.0, "B"), (13.0, 13.2, "A")]
+    got = sorted(feeder.find_overlaps(segs))
+    assert [(a, b) for a, b, _ in got] == [(4.0, 5.0), (8.7, 9.0), (13.0, 13.2)]
+    assert all(sorted(s) == ["A", "B"] for _, _, s in got)
+    kept = feeder.detect_overlap_regions(segs)                      # >= 0.50 s
+    assert [(a, b) for a, b, _ in kept] == [(4.0, 5.0)]
+    # touching segments (end == start) do not overlap: ends sort before starts at equal times
+    assert feeder.find_overlaps([(0.0, 1.0, "A"), (1.0, 2.0, "B")]) == []
+    # three speakers: the region start is not reset until at most one speaker remains
+    three = feeder.find_overlaps([(0.0, 10.0, "A"), (2.0, 4.0, "B"), (3.0, 6.0, "C")])
+    assert sorted((a, b) for a, b, _ in three) == [(2.0, 4.0), (2.0, 6.0)]
+
+
+def test_slice_indices_follow_extract_segment():
+    from clearconverse_b200 import feeder
+    assert feeder.slice_indices(0.25, 1.0, 16000, 16000) == (4000, 16000)
+    assert feeder.slice_indices(-1.0, 0.5, 16000, 16000) == (0, 8000)           # negative start clamps to 0
+    assert feeder.slice_indices(0.5, 9.0, 16000, 16000) == (8000, 16000)        # end clamps to the duration
+    assert feeder.slice_indices(0.7, 0.7, 16000, 16000) is None                 # the reference's zeros(1, 100) case
+
+
+def test_resegment_overlap_windows_votes_and_merging():
+    """_resegment_overlap (api.py:961-1050) with a scripted embedding: speaker A for the first 2.0 s of a 4.4 s segment,
+    B after; 0.8 s windows every 0.4 s; runs of equal votes fuse; the result tiles inside [seg_start, seg_end]."""
+    from clearconverse_b200 import feeder
+    cfg = feeder.FeederConfig()
+    profiles = {"A": (1.0, 0.0), "B": (0.0, 1.0)}
+    seg_start, seg_end, n = 10.0, 14.4, int(4.4 * 16000)
+    calls = []
+
+    def embed(i0, i1):
+        calls.append((i0, i1))
+        mid = 0.5 * (i0 + i1) / 16000
+        return (1.0, 0.1) if mid < 2.0 else (0.1, 1.0)
+    out = feeder.resegment_overlap(n, seg_start, seg_end, profiles, embed, cfg)
+    # windows at 0.0, 0.4, ... 3.2 s: the tenth (3.6 s) is lost to `curr += step` rounding (13.6 + 0.8 > 14.4 in
+    # binary floating point), exactly as in the reference's loop
+    assert len(calls) == 9 and calls[0] == (0, 12800) and calls[1][0] == 6400
+    assert [spk for _, _, spk in out] == ["A", "B"]
+    (a0, a1, _), (b0, b1, _) = out                                  # four A windows, five B windows; runs keep their window edges
+    assert a0 == seg_start and abs(a1 - 12.0) < 1e-9 and abs(b0 - 11.6) < 1e-9 and abs(b1 - 14.0) < 1e-9
+    # a segment shorter than one window gets a single UNKNOWN region (api.py:1013-1014)
+    assert feeder.resegment_overlap(8000, 3.0, 3.5, profiles, embed, cfg) == [(3.0, 3.5, "UNKNOWN")]
+    # no embedding available: continuity / UNKNOWN (api.py:1005-1008)
+    unk = feeder.resegment_overlap(n, seg_start, seg_end, profiles, lambda i0, i1: None, cfg)
+    assert len(unk) == 1 and unk[0][0] == seg_start and abs(unk[0][1] - 14.0) < 1e-9 and unk[0][2] == "UNKNOWN"   # one run of nine windows
+    # a narrow win over the previous window's speaker keeps the previous speaker (api.py:992-1000)
+    assert feeder._pick_speaker([("A", 0.80), ("B", 0.75)], previous="B") == ("B", 0.75)
+    assert feeder._pick_speaker([("A", 0.80), ("B", 0.40)], previous="B") == ("A", 0.80)
+    assert feeder._pick_speaker([("A", 0.80), ("B", 0.75)], previous=None) == ("A", 0.80)
+
+
+def test_separator_inputs_of_a_synthetic_meeting():
+    """The whole feeder on a synthetic one-hour two-speaker timeline: every input lies inside its diarization segment,
+    is at least 0.3 s long, and the duplicates the product separates twice collapse under dedupe_spans."""
+    from clearconverse_b200 import feeder
+    cfg = feeder.FeederConfig()
+    segments, profiles, factory = feeder.synthetic_meeting(3600.0, 0.20, seed=4)
+    n_samples = int(3600.0 * cfg.sample_rate)
+    overlapped = sum(b - a for a, b, _ in feeder.find_overlaps(segments))
+    assert 0.10 * 3600 < overlapped < 0.30 * 3600
+    inputs = feeder.separator_inputs(segments, n_samples, profiles, factory(cfg.sample_rate), cfg)
+    assert len(inputs) > 100
+    for it in inputs:
+        s0, s1, _ = it.segment
+        assert int(s0 * cfg.sample_rate) <= it.i0 < it.i1 <= int(s1 * cfg.sample_rate) + 1
+        assert (it.i1 - it.i0) >= int(0.29 * cfg.sample_rate)
+        assert it.speaker in ("SPEAKER_00", "SPEAKER_01", "UNKNOWN")
+    unique, inverse = sharding.dedupe_spans([(it.i0, it.i1) for it in inputs])
+    assert len(unique) <= len(inputs) and len(inverse) == len(inputs)
+    again = feeder.separator_inputs(segments, n_samples, profiles, factory(cfg.sample_rate), cfg)
+    assert [(i.i0, i.i1, i.speaker) for i in again] == [(i.i0, i.i1, i.speaker) for i in inputs]      # deterministic
