@@ -12,9 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libresep_b200.so")
 
 ABI_VERSION = 1
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_FP16 = 0, 1, 2, 3
 BATCH_COUPLED, BATCH_INDEPENDENT = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 BATCH_MODES = {"coupled": BATCH_COUPLED, "independent": BATCH_INDEPENDENT}
 
 E_INVAL, E_SHORT, E_CUDA, E_WORKSPACE, E_POS, E_NODEVICE = -1, -2, -3, -4, -5, -6

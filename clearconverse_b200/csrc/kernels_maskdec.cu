@@ -60,12 +60,12 @@ struct MaskDecArgs {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(md::THREADS, 1)
 k_maskdec_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmWL, const __grid_constant__ CUtensorMap tmX, const MaskDecArgs a) {
   using namespace md;
-  constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, UMMA_BF16, 128, 256);
+  constexpr uint32_t IDESC = umma_idesc(F16 ? UMMA_F16 : UMMA_BF16, F16 ? UMMA_F16 : UMMA_BF16, 128, 256);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;
@@ -319,8 +319,10 @@ int launch_maskdec(ResepHandle* h, const bf16* prelu, const float* x0, const Pla
   int rc;
   const bool split = h->w16_mode != 0;
   if ((rc = make_tmap<bf16>(h, &tmA, prelu, p.M, D, 128))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW, h->w.fc_w_bf, NSPK * D, D, 256))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmWL, split ? h->w.fc_w_bl : h->w.fc_w_bf, NSPK * D, D, 256))) return rc;
+  const bf16* w_hi = h->fmt16 ? h->w.fc_w_h[0] : h->w.fc_w_bf;
+  const bf16* w_lo = h->fmt16 ? h->w.fc_w_h[1] : h->w.fc_w_bl;
+  if ((rc = make_tmap<bf16>(h, &tmW, w_hi, NSPK * D, D, 256))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmWL, split ? w_lo : w_hi, NSPK * D, D, 256))) return rc;
   if ((rc = make_tmap<float>(h, &tmX, x0, p.M, D, 128))) return rc;
   MaskDecArgs a;
   a.fc_b = h->w.fc_b; a.dec_w = h->w.dec_w;
@@ -330,13 +332,9 @@ int launch_maskdec(ResepHandle* h, const bf16* prelu, const float* x0, const Pla
   if (a.n_tiles < 1) a.n_tiles = 1;
   const int grid = a.n_tiles < h->sm_count ? a.n_tiles : h->sm_count;
   ProfScope prof_scope(h, "k_maskdec_tc", st);
-  if (split) {
-    RESEP_CUDA(h, cudaFuncSetAttribute(k_maskdec_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, md::SMEM));
-    RESEP_CUDA(h, launch_pdl(k_maskdec_tc<true>, dim3(grid), dim3(md::THREADS), md::SMEM, st, tmA, tmW, tmWL, tmX, a));
-  } else {
-    RESEP_CUDA(h, cudaFuncSetAttribute(k_maskdec_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, md::SMEM));
-    RESEP_CUDA(h, launch_pdl(k_maskdec_tc<false>, dim3(grid), dim3(md::THREADS), md::SMEM, st, tmA, tmW, tmWL, tmX, a));
-  }
+  auto kern = h->fmt16 ? (split ? k_maskdec_tc<true, true> : k_maskdec_tc<false, true>) : (split ? k_maskdec_tc<true, false> : k_maskdec_tc<false, false>);
+  RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, md::SMEM));
+  RESEP_CUDA(h, launch_pdl(kern, dim3(grid), dim3(md::THREADS), md::SMEM, st, tmA, tmW, tmWL, tmX, a));
   RESEP_LAUNCH_CHECK(h, "k_maskdec_tc");
   return RESEP_OK;
 }

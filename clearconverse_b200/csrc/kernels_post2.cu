@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t sw128_f32_off(int row, int col) {   // fp32 
   return (uint32_t)((col >> 5) * post2::ATOM + row * 128 + ((((col & 31) >> 2) ^ (row & 7)) << 4));
 }
 
-template <bool SPLIT, bool SPLIT_FFN>
+template <bool SPLIT, bool SPLIT_FFN, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(post2::THREADS, 1)
 k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmO,
            const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWoL,
@@ -109,7 +109,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   using namespace post2;
   constexpr int PARTS = SPLIT ? 2 : 1;          // out-proj weight operand: bf16 hi (+ lo)
   constexpr int FPARTS = SPLIT_FFN ? 2 : 1;     // FFN weight operands
-  constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, UMMA_BF16, 256, 128);
+  constexpr uint32_t IDESC = umma_idesc(F16 ? UMMA_F16 : UMMA_BF16, F16 ? UMMA_F16 : UMMA_BF16, 256, 128);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   float* par = reinterpret_cast<float*>(smem + OFF_PAR);
@@ -427,8 +427,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
           // y = ((x - mean) * rstd) * g + e
           const float2 y0 = ffma2(ffma2(v[2 * j], rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
           const float2 y1 = ffma2(ffma2(v[2 * j + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
-          p[2 * jj] = pack_bf16(y0.x, y0.y);
-          p[2 * jj + 1] = pack_bf16(y1.x, y1.y);
+          p[2 * jj] = pack16<F16>(y0.x, y0.y);
+          p[2 * jj + 1] = pack16<F16>(y1.x, y1.y);
         }
         tmem_st16(lane_base + TM_Y2 + 64 * (t & 1) + 32 * hf + 16 * h2, p);
       }
@@ -457,8 +457,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias + 32 * h2 + 4 * j);
           const float2 x0 = fadd2(v[2 * j], make_float2(b4.x, b4.y)), x1 = fadd2(v[2 * j + 1], make_float2(b4.z, b4.w));
-          p[2 * j] = pack_bf16_relu(x0.x, x0.y);
-          p[2 * j + 1] = pack_bf16_relu(x1.x, x1.y);
+          p[2 * j] = pack16_relu<F16>(x0.x, x0.y);
+          p[2 * j + 1] = pack16_relu<F16>(x1.x, x1.y);
         }
         tmem_st16(hcol + 16 * h2, p);        // this thread's own 64 fp32 columns -> their first 32 columns, packed
       }
@@ -558,12 +558,13 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
   int rc;
   if ((rc = make_tmap<bf16>(h, &tmCtx, ctx, rows, D, 128))) return rc;
   if ((rc = make_tmap<float>(h, &tmO, o, rows, D, 128))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmWo, lw.out_w_bf, D, D, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmWoL, lw.out_w_bl, D, D, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW1, lw.f1_w_bf, FFN, D, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW1L, lw.f1_w_bl, FFN, D, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW2, lw.f2_w_bf, D, FFN, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW2L, lw.f2_w_bl, D, FFN, 64))) return rc;
+  const bool f16 = h->fmt16 != 0;
+  if ((rc = make_tmap<bf16>(h, &tmWo, f16 ? lw.out_w_h[0] : lw.out_w_bf, D, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmWoL, f16 ? lw.out_w_h[1] : lw.out_w_bl, D, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW1, f16 ? lw.f1_w_h[0] : lw.f1_w_bf, FFN, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW1L, f16 ? lw.f1_w_h[1] : lw.f1_w_bl, FFN, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW2, f16 ? lw.f2_w_h[0] : lw.f2_w_bf, D, FFN, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW2L, f16 ? lw.f2_w_h[1] : lw.f2_w_bl, D, FFN, 64))) return rc;
   static long long* trace_buf = nullptr;
   if (getenv("RESEP_TRACE") && !trace_buf) { cudaMalloc(&trace_buf, 1536 * 8); cudaMemset(trace_buf, 0, 1536 * 8); g_post_trace = trace_buf; }
   static const int dbg = getenv("RESEP_DBG") ? atoi(getenv("RESEP_DBG")) : 0;
@@ -571,7 +572,8 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
   std::memcpy(a.bo, lw.h_post_par, D * 4); std::memcpy(a.g2, lw.h_post_par + D, D * 4); std::memcpy(a.be2, lw.h_post_par + 2 * D, D * 4);
   std::memcpy(a.b2, lw.h_post_par + 3 * D, D * 4); std::memcpy(a.b1, lw.h_post_par + 4 * D, FFN * 4);
   a.M = rows; a.dbg = dbg; a.trace = trace_buf;
-  auto kern = split_ffn ? k_post2_tc<true, true> : split ? k_post2_tc<true, false> : k_post2_tc<false, false>;
+  auto kern = f16 ? (split_ffn ? k_post2_tc<true, true, true> : split ? k_post2_tc<true, false, true> : k_post2_tc<false, false, true>)
+                  : (split_ffn ? k_post2_tc<true, true, false> : split ? k_post2_tc<true, false, false> : k_post2_tc<false, false, false>);
   RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, post2::SMEM));
   static int max_pairs = 0;                // CTA pairs the device can hold at once (one CTA per SM)
   if (max_pairs == 0) {

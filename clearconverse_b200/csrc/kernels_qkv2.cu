@@ -60,14 +60,14 @@ __device__ __forceinline__ uint32_t sw128_bf16_q(int row, int col) {   // 16-byt
   return (uint32_t)((col >> 6) * qkv2::ATOM + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(qkv2::THREADS, 1)
 k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmW,
           const __grid_constant__ CUtensorMap tmWL, const __grid_constant__ CUtensorMap tmQ,
           const __grid_constant__ Qkv2Args args) {
   using namespace qkv2;
   constexpr int PARTS = SPLIT ? 2 : 1;
-  constexpr uint32_t IDESC = umma_idesc(UMMA_BF16, UMMA_BF16, 256, 128);
+  constexpr uint32_t IDESC = umma_idesc(F16 ? UMMA_F16 : UMMA_BF16, F16 ? UMMA_F16 : UMMA_BF16, 256, 128);
   extern __shared__ __align__(1024) uint8_t smem[];
   float* s_sum = reinterpret_cast<float*>(smem + OFF_RED);
   float* s_sq = s_sum + 256;
@@ -209,8 +209,8 @@ k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUten
           const int c = 64 * hf + 4 * j;
           const float2 y0 = ffma2(ffma2(v[2 * j], rs2, nm2), make_float2(args.g1[c], args.g1[c + 1]), make_float2(args.be1[c], args.be1[c + 1]));
           const float2 y1 = ffma2(ffma2(v[2 * j + 1], rs2, nm2), make_float2(args.g1[c + 2], args.g1[c + 3]), make_float2(args.be1[c + 2], args.be1[c + 3]));
-          p[2 * jj] = pack_bf16(y0.x, y0.y);
-          p[2 * jj + 1] = pack_bf16(y1.x, y1.y);
+          p[2 * jj] = pack16<F16>(y0.x, y0.y);
+          p[2 * jj + 1] = pack16<F16>(y1.x, y1.y);
         }
         tmem_st16(lane_base + TM_Y2 + 64 * b + 32 * hf + 16 * h2, p);
       }
@@ -259,7 +259,7 @@ k_qkv2_tc(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUten
             for (int i = 0; i < 4; ++i)
               x[i] = fadd2(v[4 * j + i], make_float2(args.bin[n * 128 + cb + 8 * j + 2 * i], args.bin[n * 128 + cb + 8 * j + 2 * i + 1]));
             *reinterpret_cast<uint4*>(out + sw128_bf16_q(r, cb + 8 * j)) =
-                make_uint4(pack_bf16(x[0].x, x[0].y), pack_bf16(x[1].x, x[1].y), pack_bf16(x[2].x, x[2].y), pack_bf16(x[3].x, x[3].y));
+                make_uint4(pack16<F16>(x[0].x, x[0].y), pack16<F16>(x[1].x, x[1].y), pack16<F16>(x[2].x, x[2].y), pack16<F16>(x[3].x, x[3].y));
           }
           fence_proxy_async();
           dbar();
@@ -292,14 +292,14 @@ int launch_qkv2_tc(ResepHandle* h, const LayerDev& lw, const float* o, bf16* qkv
   CUtensorMap tmO, tmW, tmWL, tmQ;
   int rc;
   if ((rc = make_tmap<float>(h, &tmO, o, rows, D, 128))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmW, lw.in_w_bf, 3 * D, D, 64))) return rc;
-  if ((rc = make_tmap<bf16>(h, &tmWL, lw.in_w_bl, 3 * D, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmW, h->fmt16 ? lw.in_w_h[0] : lw.in_w_bf, 3 * D, D, 64))) return rc;
+  if ((rc = make_tmap<bf16>(h, &tmWL, h->fmt16 ? lw.in_w_h[1] : lw.in_w_bl, 3 * D, D, 64))) return rc;
   if ((rc = make_tmap<bf16>(h, &tmQ, qkv, rows, 3 * D, 128))) return rc;
   Qkv2Args a;
   std::memcpy(a.bin, lw.h_in_b, 3 * D * 4);
   std::memcpy(a.g1, lw.h_in_b + 3 * D, D * 4); std::memcpy(a.be1, lw.h_in_b + 4 * D, D * 4);
   a.M = rows;
-  auto kern = split ? k_qkv2_tc<true> : k_qkv2_tc<false>;
+  auto kern = h->fmt16 ? (split ? k_qkv2_tc<true, true> : k_qkv2_tc<false, true>) : (split ? k_qkv2_tc<true, false> : k_qkv2_tc<false, false>);
   RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, qkv2::SMEM));
   const int max_pairs = h->sm_count / 2;
   const int ptiles = (int)((rows + 255) / 256);

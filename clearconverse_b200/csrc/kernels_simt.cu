@@ -10,6 +10,8 @@
 //   attention    nn.MultiheadAttention (8 heads x 16), no masks, softmax over all keys
 //   epilogue     TransformerEncoder.norm + dual_path.GlobalLayerNorm + skip; `output.mean(1)`
 //   decoder      mask apply + dual_path.Decoder (ConvTranspose1d 128->1, k16, s8) + pad/crop
+#include <cuda_fp16.h>
+
 #include "resep_internal.cuh"
 
 namespace resep {
@@ -150,6 +152,14 @@ __device__ __forceinline__ void store4(bf16* p, float4 v) {
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
 
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* 
                                                                    const float* __restrict__ fn_b, const float* __restrict__ gln_w,
                                                                    const float* __restrict__ gln_b, const float* xin, float* out,
                                                                    float* __restrict__ seq_mean, int seq_len,
-                                                                   bf16* __restrict__ prelu_out, const float* __restrict__ prelu_a) {
+                                                                   bf16* __restrict__ prelu_out, const float* __restrict__ prelu_a, int f16) {
   extern __shared__ __align__(16) float ys[];            // [seq_len][128]
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL successor (k_maskdec_tc) may set up meanwhile
   __shared__ double red[2][EPI_T / 32];
@@ -565,7 +575,8 @@ __global__ void __launch_bounds__(EPI_T, 2) k_block_epilogue_chunk(const float* 
       float4 pz;
       pz.x = v.x >= 0.f ? v.x : slope * v.x; pz.y = v.y >= 0.f ? v.y : slope * v.y;
       pz.z = v.z >= 0.f ? v.z : slope * v.z; pz.w = v.w >= 0.f ? v.w : slope * v.w;
-      store4(prelu_out + idx * 4, pz);
+      if (f16) store4(reinterpret_cast<__half*>(prelu_out) + idx * 4, pz);   // (fp16 mode: the 16-bit container holds IEEE halves)
+      else store4(prelu_out + idx * 4, pz);
     }
   }
   if (seq_mean != nullptr) {
@@ -588,7 +599,7 @@ int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const flo
   if (seq_off == nullptr && seq_len <= CHUNK) {
     const size_t smem = (size_t)seq_len * D * sizeof(float);
     RESEP_CUDA(h, cudaFuncSetAttribute(k_block_epilogue_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, CHUNK * D * (int)sizeof(float)));
-    k_block_epilogue_chunk<<<(unsigned)n_seq, EPI_T, smem, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, prelu_out, prelu_a);
+    k_block_epilogue_chunk<<<(unsigned)n_seq, EPI_T, smem, st>>>(o, fn_w, fn_b, gln_w, gln_b, xin, out, seq_mean, seq_len, prelu_out, prelu_a, h->fmt16);
     RESEP_LAUNCH_CHECK(h, "k_block_epilogue_chunk");
     return RESEP_OK;
   }
@@ -602,6 +613,7 @@ int launch_block_epilogue(ResepHandle* h, float* o, const float* fn_w, const flo
     int64_t rows = 0;
     if (seq_off == nullptr) rows = (int64_t)n_seq * seq_len;
     else return set_err(h, RESEP_EINVAL, "block epilogue: fused PReLU needs equal-length sequences");
+    if (h->fmt16) return launch_prelu_t<__half>(h, out, prelu_a, reinterpret_cast<__half*>(prelu_out), rows * D, st);
     return launch_prelu_t<bf16>(h, out, prelu_a, prelu_out, rows * D, st);
   }
   return RESEP_OK;
@@ -635,6 +647,7 @@ int launch_prelu_t(ResepHandle* h, const float* x, const float* a, OutT* y, int6
 }
 template int launch_prelu_t<float>(ResepHandle*, const float*, const float*, float*, int64_t, cudaStream_t);
 template int launch_prelu_t<bf16>(ResepHandle*, const float*, const float*, bf16*, int64_t, cudaStream_t);
+template int launch_prelu_t<__half>(ResepHandle*, const float*, const float*, __half*, int64_t, cudaStream_t);
 int launch_prelu(ResepHandle* h, const float* x, const float* a, float* y, int64_t n, cudaStream_t st) {
   return launch_prelu_t<float>(h, x, a, y, n, st);
 }

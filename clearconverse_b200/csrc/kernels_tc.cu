@@ -62,12 +62,13 @@ template <typename TIn, int EPI, bool SPLITW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
           const __grid_constant__ CUtensorMap tmWlo, const float* __restrict__ bias, void* out_, int64_t M, int N, int K,
-          int relu) {
+          int relu, int f16) {
   constexpr int STAGE_BYTES = stage_bytes(SPLITW);
   constexpr int BK = 128 / sizeof(TIn);               // elements per 128-byte swizzle row: 64 bf16 / 32 tf32
   constexpr int UK = 32 / sizeof(TIn);                // K per tcgen05.mma: 16 bf16 / 8 tf32
-  constexpr uint32_t FMT = sizeof(TIn) == 2 ? UMMA_BF16 : UMMA_TF32;
-  constexpr uint32_t IDESC = umma_idesc(FMT, FMT, BM, BN);
+  // 16-bit operands: bf16 or (f16 != 0) IEEE fp16 -- same instruction, another format field
+  const uint32_t FMT = sizeof(TIn) == 2 ? (f16 ? UMMA_F16 : UMMA_BF16) : UMMA_TF32;
+  const uint32_t IDESC = umma_idesc(FMT, FMT, BM, BN);
 
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -184,8 +185,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 f[i] = __uint_as_float(v[j + i]) + __ldg(bp + j + i);
                 if (relu) f[i] = fmaxf(f[i], 0.f);
               }
-              op[j / 8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                     pack_bf16(f[6], f[7]));
+              op[j / 8] = f16 ? make_uint4(pack16<true>(f[0], f[1]), pack16<true>(f[2], f[3]), pack16<true>(f[4], f[5]), pack16<true>(f[6], f[7]))
+                              : make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
             }
           } else {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + row * N + n0 + c0);
@@ -240,7 +241,7 @@ static int launch_gemm_tc(ResepHandle* h, const TIn* A, const TIn* W, const floa
   static const std::string kname = std::string("k_gemm_tc<") + (sizeof(TIn) == 2 ? "bf16" : "tf32") + "," + kEpiName[EPI] +
                                    (SPLITW ? ",hi+lo>" : ">");
   ProfScope prof_scope(h, kname.c_str(), st);
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, tmWlo, bias, out, M, N, K, relu ? 1 : 0);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, tmWlo, bias, out, M, N, K, relu ? 1 : 0, sizeof(TIn) == 2 ? h->fmt16 : 0);
   RESEP_LAUNCH_CHECK(h, "k_gemm_tc");
   return RESEP_OK;
 }
@@ -262,6 +263,7 @@ static int gemm_bf16(ResepHandle* h, int mode, const bf16* A, const bf16* W, con
 constexpr int AKT = 160;        // keys per tile == queries per CTA
 constexpr int KS_STRIDE = 24;   // halves
 constexpr int VT_STRIDE = AKT + 8;
+template <bool F16>
 __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int seq_len,
                                                         const int* __restrict__ seq_off, const int* __restrict__ tile_seq,
                                                         const int* __restrict__ tile_q0) {
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
       for (int j = 0; j < AKT / 8; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         const uint32_t* kp = reinterpret_cast<const uint32_t*>(Ks + (8 * j + g) * KS_STRIDE);
-        mma_bf16_16816(s[j], qa[mt], kp[t4], kp[t4 + 4]);
+        mma16_16816<F16>(s[j], qa[mt], kp[t4], kp[t4 + 4]);
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -379,14 +381,14 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 #pragma unroll
       for (int kk = 0; kk < AKT / 16; ++kk) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        pa[0] = pack16<F16>(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack16<F16>(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack16<F16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack16<F16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
         for (int nn = 0; nn < 2; ++nn) {
           const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vt + (8 * nn + g) * VT_STRIDE + 16 * kk);
-          mma_bf16_16816(o[mt][nn], pa, vp[t4], vp[t4 + 4]);
+          mma16_16816<F16>(o[mt][nn], pa, vp[t4], vp[t4 + 4]);
         }
       }
     }
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(160) k_attention_bf16(const bf16* __restrict__
 #pragma unroll
         for (int nn = 0; nn < 2; ++nn)
           *reinterpret_cast<uint32_t*>(op + 8 * nn + 2 * t4) =
-              pack_bf16(o[mt][nn][2 * hh] * inv, o[mt][nn][2 * hh + 1] * inv);
+              pack16<F16>(o[mt][nn][2 * hh] * inv, o[mt][nn][2 * hh + 1] * inv);
       }
     }
   }
@@ -428,25 +430,24 @@ constexpr int AS_ROW = 24;   // halves per staged K / V row (16 used)
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// Squared norms for the softmax stabiliser, accumulated in packed bf16 (HFMA2.BF16: two elements per instruction, no
-// conversions).  Only an upper bound is needed downstream; the roundings are covered by the 1.02 margin there.
-__device__ __forceinline__ float sqnorm16_bf16(const uint32_t (&w)[8]) {
-  __nv_bfloat162 acc = __floats2bfloat162_rn(0.f, 0.f);
+// Squared norms for the softmax stabiliser, accumulated in the packed 16-bit operand format (HFMA2: two elements per
+// instruction, no conversions).  Only an upper bound is needed downstream; the roundings are covered by the 1.02 margin.
+// (An fp16 sum that overflows becomes inf, which selects the exact-row-maximum path.)
+template <bool F16>
+__device__ __forceinline__ float sqnorm16_h(const uint32_t (&w)[8]) {
+  uint32_t acc = 0u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    acc = __hfma2(v, v, acc);
-  }
-  const float2 f = __bfloat1622float2(acc);
+  for (int i = 0; i < 8; ++i) acc = hfma2_sq<F16>(w[i], acc);
+  const float2 f = unpack16<F16>(acc);
   return f.x + f.y;
 }
-__device__ __forceinline__ float sqnorm4_bf16(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&a), vb = *reinterpret_cast<const __nv_bfloat162*>(&b);
-  const float2 f = __bfloat1622float2(__hfma2(vb, vb, __hmul2(va, va)));
+template <bool F16>
+__device__ __forceinline__ float sqnorm4_h(uint32_t a, uint32_t b) {
+  const float2 f = unpack16<F16>(hfma2_sq<F16>(b, hfma2_sq<F16>(a, 0u)));
   return f.x + f.y;
 }
 
-template <int KMAX, int WARPS, int MT>
+template <int KMAX, int WARPS, int MT, bool F16>
 __global__ void __launch_bounds__(32 * WARPS, KMAX <= 160 ? 6 : 2)
 k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int seq_len, const int* __restrict__ seq_off,
                        int q_tiles) {
@@ -503,7 +504,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       kd[0] = k0; kd[1] = k1;
       vd[0] = v0; vd[1] = v1;
       const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-      kn2max = fmaxf(kn2max, sqnorm16_bf16(kw));     // (same arithmetic as k_attention_bf16_tma: the two kernels must agree bit for bit)
+      kn2max = fmaxf(kn2max, sqnorm16_h<F16>(kw));     // (same arithmetic as k_attention_bf16_tma: the two kernels must agree bit for bit)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kn2max = fmaxf(kn2max, __shfl_xor_sync(0xffffffffu, kn2max, o));
@@ -518,7 +519,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
   const int lm = lane >> 3, lr = lane & 7;
   const bf16* k_lane = Ks + ((lm >> 1) * 8 + lr) * AS_ROW + (lm & 1) * 8;   // K: m0/m1 = dh halves of tile A, m2/m3 of tile B
   const bf16* v_lane = Vs + ((lm & 1) * 8 + lr) * AS_ROW + (lm >> 1) * 8;   // V^T: m0/m1 = key halves for dh 0-7, m2/m3 for dh 8-15
-  constexpr uint32_t ONES = 0x3F803F80u;              // bf16 (1.0, 1.0): B fragment of an all-ones [16 keys x 8] matrix
+  constexpr uint32_t ONES = F16 ? 0x3C003C00u : 0x3F803F80u;              // bf16 (1.0, 1.0): B fragment of an all-ones [16 keys x 8] matrix
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int row0 = q0 + warp * (16 * MT) + mt * 16;
@@ -530,8 +531,8 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
     // violate that (never seen with LayerNorm'ed inputs) takes the exact row-maximum pass instead.
     float qn0, qn1;
     {
-      qn0 = sqnorm4_bf16(qa[0], qa[2]);               // row g:     dims 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
-      qn1 = sqnorm4_bf16(qa[1], qa[3]);               // row g + 8
+      qn0 = sqnorm4_h<F16>(qa[0], qa[2]);               // row g:     dims 2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4
+      qn1 = sqnorm4_h<F16>(qa[1], qa[3]);               // row g + 8
       qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
@@ -547,8 +548,8 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       uint32_t kf[4];
       ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
       float s0[4], s1[4];
-      mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
-      mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
+      mma16_16816_z<F16>(s0, qa, kf[0], kf[1]);
+      mma16_16816_z<F16>(s1, qa, kf[2], kf[3]);
       if (MASK) {
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
@@ -580,8 +581,8 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
       ldmatrix_x4(kf, k_lane + kk * 16 * AS_ROW);
       ldmatrix_x4_trans(vf, v_lane + kk * 16 * AS_ROW);
       float s0[4], s1[4];
-      mma_bf16_16816_c(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
-      mma_bf16_16816_c(s1, qa, kf[2], kf[3], nb0, nb1);
+      mma16_16816_c<F16>(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
+      mma16_16816_c<F16>(s1, qa, kf[2], kf[3], nb0, nb1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s0[i] = ex2_approx(s0[i]); s1[i] = ex2_approx(s1[i]); }
       if (MASK) {
@@ -592,13 +593,13 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
         if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
       }
       uint32_t pa[4];
-      pa[0] = pack_bf16(s0[0], s0[1]);
-      pa[1] = pack_bf16(s0[2], s0[3]);
-      pa[2] = pack_bf16(s1[0], s1[1]);
-      pa[3] = pack_bf16(s1[2], s1[3]);
-      mma_bf16_16816(o0, pa, vf[0], vf[1]);
-      mma_bf16_16816(o1, pa, vf[2], vf[3]);
-      mma_bf16_16816(ol, pa, ONES, ONES);
+      pa[0] = pack16<F16>(s0[0], s0[1]);
+      pa[1] = pack16<F16>(s0[2], s0[3]);
+      pa[2] = pack16<F16>(s1[0], s1[1]);
+      pa[3] = pack16<F16>(s1[2], s1[3]);
+      mma16_16816<F16>(o0, pa, vf[0], vf[1]);
+      mma16_16816<F16>(o1, pa, vf[2], vf[3]);
+      mma16_16816<F16>(ol, pa, ONES, ONES);
     };
 #pragma unroll 3
     for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
@@ -607,13 +608,13 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
     const int r0 = row0 + g, r1 = row0 + g + 8;
     if (r0 < len) {
       bf16* op = ctx + (int64_t)(off + r0) * D + head * DH + 2 * t4;
-      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[0] * i0, o0[1] * i0);
-      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[0] * i0, o1[1] * i0);
+      *reinterpret_cast<uint32_t*>(op) = pack16<F16>(o0[0] * i0, o0[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack16<F16>(o1[0] * i0, o1[1] * i0);
     }
     if (r1 < len) {
       bf16* op = ctx + (int64_t)(off + r1) * D + head * DH + 2 * t4;
-      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[2] * i1, o0[3] * i1);
-      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[2] * i1, o1[3] * i1);
+      *reinterpret_cast<uint32_t*>(op) = pack16<F16>(o0[2] * i1, o0[3] * i1);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack16<F16>(o1[2] * i1, o1[3] * i1);
     }
   }
 }
@@ -628,6 +629,7 @@ k_attention_bf16_short(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int
 // (+ 32 B of the next head, unused; zero-filled past column 384), 128B-swizzled so ldmatrix reads it conflict-free.
 // Rows past the sequence inside a box belong to the next chunk: as keys they are masked (last block), as queries
 // they are computed and never stored; past the end of the tensor TMA fills zeros.
+template <bool F16>
 __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx,
                                                                 int seq_len) {
   __shared__ __align__(1024) bf16 Ts[160 * 64];      // row r: 16-byte chunk c at c ^ (r & 7); chunks 0,1 = q, 2,3 = k, 4,5 = v
@@ -655,7 +657,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     const uint4 ka = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((2 ^ r7) << 3));
     const uint4 kb = *reinterpret_cast<const uint4*>(Ts + threadIdx.x * 64 + ((3 ^ r7) << 3));
     const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-    float kn2 = sqnorm16_bf16(kw);
+    float kn2 = sqnorm16_h<F16>(kw);
     if ((int)threadIdx.x >= len) kn2 = 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kn2 = fmaxf(kn2, __shfl_xor_sync(0xffffffffu, kn2, o));
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
   __syncthreads();
   const float kmax2 = fmaxf(fmaxf(fmaxf(s_kmax[0], s_kmax[1]), fmaxf(s_kmax[2], s_kmax[3])), s_kmax[4]);
   const int nkk = (len + 15) >> 4;
-  constexpr uint32_t ONES = 0x3F803F80u;
+  constexpr uint32_t ONES = F16 ? 0x3C003C00u : 0x3F803F80u;
   // ldmatrix lane addressing in the [rows x 128 B] tile with the 128B swizzle: matrix m = lane / 8, row lane % 8;
   // every row base below is a multiple of 8, so the swizzle term is lane % 8
   const int lm = lane >> 3, lr = lane & 7;
@@ -680,8 +682,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     // softmax stabiliser from the Cauchy-Schwarz bound (see k_attention_bf16_short); exact row maxima as fallback
     float qn0, qn1;
     {
-      qn0 = sqnorm4_bf16(qa[0], qa[2]);               // row g:     a0 (k 0-1 of this lane's quad), a2 (k 8-9)
-      qn1 = sqnorm4_bf16(qa[1], qa[3]);               // row g + 8: a1, a3
+      qn0 = sqnorm4_h<F16>(qa[0], qa[2]);               // row g:     a0 (k 0-1 of this lane's quad), a2 (k 8-9)
+      qn1 = sqnorm4_h<F16>(qa[1], qa[3]);               // row g + 8: a1, a3
       qn0 += __shfl_xor_sync(0xffffffffu, qn0, 1); qn0 += __shfl_xor_sync(0xffffffffu, qn0, 2);
       qn1 += __shfl_xor_sync(0xffffffffu, qn1, 1); qn1 += __shfl_xor_sync(0xffffffffu, qn1, 2);
     }
@@ -695,8 +697,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
         uint32_t kf[4];
         ldmatrix_x4(kf, k_lane + kk * 16 * 64);
         float s0[4], s1[4];
-        mma_bf16_16816_z(s0, qa, kf[0], kf[1]);
-        mma_bf16_16816_z(s1, qa, kf[2], kf[3]);
+        mma16_16816_z<F16>(s0, qa, kf[0], kf[1]);
+        mma16_16816_z<F16>(s1, qa, kf[2], kf[3]);
         const int c = kk * 16 + 2 * t4;
         if (c >= len) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
         if (c + 1 >= len) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
@@ -718,8 +720,8 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
       ldmatrix_x4(kf, k_lane + kk * 16 * 64);
       ldmatrix_x4_trans(vf, v_lane + kk * 16 * 64);
       float s0[4], s1[4];
-      mma_bf16_16816_c(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
-      mma_bf16_16816_c(s1, qa, kf[2], kf[3], nb0, nb1);
+      mma16_16816_c<F16>(s0, qa, kf[0], kf[1], nb0, nb1);   // s - stabiliser, straight out of the tensor core
+      mma16_16816_c<F16>(s1, qa, kf[2], kf[3], nb0, nb1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s0[i] = ex2_approx(s0[i]); s1[i] = ex2_approx(s1[i]); }
       if (MASK) {
@@ -730,13 +732,13 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
         if (c + 9 >= len) { s1[1] = 0.f; s1[3] = 0.f; }
       }
       uint32_t pa[4];
-      pa[0] = pack_bf16(s0[0], s0[1]);
-      pa[1] = pack_bf16(s0[2], s0[3]);
-      pa[2] = pack_bf16(s1[0], s1[1]);
-      pa[3] = pack_bf16(s1[2], s1[3]);
-      mma_bf16_16816(o0, pa, vf[0], vf[1]);
-      mma_bf16_16816(o1, pa, vf[2], vf[3]);
-      mma_bf16_16816(ol, pa, ONES, ONES);              // row sums of the bf16-rounded P (every column is the row sum)
+      pa[0] = pack16<F16>(s0[0], s0[1]);
+      pa[1] = pack16<F16>(s0[2], s0[3]);
+      pa[2] = pack16<F16>(s1[0], s1[1]);
+      pa[3] = pack16<F16>(s1[2], s1[3]);
+      mma16_16816<F16>(o0, pa, vf[0], vf[1]);
+      mma16_16816<F16>(o1, pa, vf[2], vf[3]);
+      mma16_16816<F16>(ol, pa, ONES, ONES);              // row sums of the bf16-rounded P (every column is the row sum)
     };
 #pragma unroll 3
     for (int kk = 0; kk < nkk - 1; ++kk) pv_block(kk, std::false_type{});
@@ -745,13 +747,13 @@ __global__ void __launch_bounds__(160, 6) k_attention_bf16_tma(const __grid_cons
     const int r0 = row0 + g, r1 = row0 + g + 8;
     if (r0 < len) {
       bf16* op = ctx + (off + r0) * D + head * DH + 2 * t4;
-      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[0] * i0, o0[1] * i0);
-      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[0] * i0, o1[1] * i0);
+      *reinterpret_cast<uint32_t*>(op) = pack16<F16>(o0[0] * i0, o0[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack16<F16>(o1[0] * i0, o1[1] * i0);
     }
     if (r1 < len) {
       bf16* op = ctx + (off + r1) * D + head * DH + 2 * t4;
-      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[2] * i1, o0[3] * i1);
-      *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[2] * i1, o1[3] * i1);
+      *reinterpret_cast<uint32_t*>(op) = pack16<F16>(o0[2] * i1, o0[3] * i1);
+      *reinterpret_cast<uint32_t*>(op + 8) = pack16<F16>(o1[2] * i1, o1[3] * i1);
     }
   }
 }
@@ -978,6 +980,7 @@ static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int
   if (intra && use_tc && tile_seq == nullptr && seq_len == CHUNK && (int64_t)n_seq * seq_len < 2000000000LL)
     return launch_attn_tc(h, qkv, ctx, n_seq, st);
   const int longest = tile_seq == nullptr ? seq_len : max_len;
+  const bool f16 = h->fmt16 != 0;
   ProfScope prof_scope(h, longest <= 160 ? (tile_seq == nullptr ? "k_attention_bf16_tma" : "k_attention_bf16_short") : longest <= 448 ? "k_attention_bf16_mid" : "k_attention_bf16", st);
   // ragged case: the plan's tile list is cut in 128-row tiles for the fp32 kernel; this kernel covers
   // 160 rows per CTA, so a 128-row tile list still covers every row (rows 128..159 of a tile repeat work
@@ -989,28 +992,30 @@ static int launch_attention_bf16(ResepHandle* h, const bf16* qkv, bf16* ctx, int
       CUtensorMap tmQKV;
       int rc = make_tmap_head(h, &tmQKV, qkv, (int64_t)n_seq * seq_len, 3 * D, 160);
       if (rc) return rc;
-      RESEP_CUDA(h, launch_pdl(k_attention_bf16_tma, dim3((unsigned)n_seq, NH), dim3(160), 0, st, tmQKV, ctx, seq_len));
+      RESEP_CUDA(h, launch_pdl(f16 ? k_attention_bf16_tma<true> : k_attention_bf16_tma<false>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, tmQKV, ctx, seq_len));
     } else if (seq_len <= 160) {
-      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<160, 5, 2>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len,
+      RESEP_CUDA(h, launch_pdl(f16 ? k_attention_bf16_short<160, 5, 2, true> : k_attention_bf16_short<160, 5, 2, false>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, seq_len,
                                (const int*)nullptr, 1));
     } else if (seq_len <= 448) {
       const int qt = (seq_len + 63) / 64;
-      RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<448, 4, 1>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, seq_len,
+      RESEP_CUDA(h, launch_pdl(f16 ? k_attention_bf16_short<448, 4, 1, true> : k_attention_bf16_short<448, 4, 1, false>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, seq_len,
                                (const int*)nullptr, qt));
     } else {
       const int tps = (seq_len + AKT - 1) / AKT;
-      k_attention_bf16<<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
+      if (f16) k_attention_bf16<true><<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
+      else k_attention_bf16<false><<<dim3((unsigned)(n_seq * tps), NH), 160, 0, st>>>(qkv, ctx, seq_len, nullptr, nullptr, nullptr);
     }
   } else if (max_len <= 160) {
     if (n_seq == 0) return RESEP_OK;
-    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<160, 5, 2>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, 0, seq_off, 1));
+    RESEP_CUDA(h, launch_pdl(f16 ? k_attention_bf16_short<160, 5, 2, true> : k_attention_bf16_short<160, 5, 2, false>, dim3((unsigned)n_seq, NH), dim3(160), 0, st, qkv, ctx, 0, seq_off, 1));
   } else if (max_len <= 448) {
     if (n_seq == 0) return RESEP_OK;
     const int qt = (max_len + 63) / 64;
-    RESEP_CUDA(h, launch_pdl(k_attention_bf16_short<448, 4, 1>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, 0, seq_off, qt));
+    RESEP_CUDA(h, launch_pdl(f16 ? k_attention_bf16_short<448, 4, 1, true> : k_attention_bf16_short<448, 4, 1, false>, dim3((unsigned)(n_seq * qt), NH), dim3(128), 0, st, qkv, ctx, 0, seq_off, qt));
   } else {
     if (n_tiles128 == 0) return RESEP_OK;
-    k_attention_bf16<<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
+    if (f16) k_attention_bf16<true><<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
+    else k_attention_bf16<false><<<dim3((unsigned)n_tiles128, NH), 160, 0, st>>>(qkv, ctx, 0, seq_off, tile_seq, tile_q0);
   }
   RESEP_LAUNCH_CHECK(h, "k_attention_bf16");
   return RESEP_OK;
@@ -1084,6 +1089,11 @@ int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int
     bf16 *yb = reinterpret_cast<bf16*>(y), *qb = reinterpret_cast<bf16*>(qkv), *cb = reinterpret_cast<bf16*>(ctx),
          *hb = reinterpret_cast<bf16*>(hid);
     static const bool fused = !(getenv("RESEP_FUSED") && getenv("RESEP_FUSED")[0] == '0');
+    if (h->fmt16) {   // the fp16 mode exists as instances of the CTA-pair kernels and the attention kernels only
+      if ((rc = launch_qkv2_tc(h, lw, o, qb, rows, st))) return rc;
+      if ((rc = launch_attention_bf16(h, qb, cb, n_seq, seq_len, seq_off, tile_seq, tile_q0, n_tiles, max_seq_len, st, intra))) return rc;
+      return launch_post2_tc(h, lw, cb, o, rows, st);
+    }
     if (fused) {
       static const bool qkv2 = !(getenv("RESEP_QKV2") && getenv("RESEP_QKV2")[0] == '0');
       if ((rc = qkv2 ? launch_qkv2_tc(h, lw, o, qb, rows, st) : launch_qkv_tc(h, lw, o, qb, rows, st))) return rc;   // norm1 + in-projection in one kernel
@@ -1120,8 +1130,9 @@ int tc_run_mask(ResepHandle* h, const float* a, float* y_scratch, float* mask, i
   if (precision == RESEP_PREC_BF16) {
     bf16* yb = reinterpret_cast<bf16*>(y_scratch);
     if (!prelu_done && (rc = launch_prelu_t<bf16>(h, a, h->w.prelu_a, yb, M * D, st))) return rc;
-    return gemm_bf16<EPI_STORE_F32>(h, h->w16_mode, yb, h->w.fc_w_bf, h->w.fc_w_bl, h->w.fc_b, mask, M, NSPK * D, D,
-                                   true, st);
+    if (h->fmt16 && !prelu_done) return set_err(h, RESEP_EINVAL, "fp16 mode: the mask GEMM expects the block epilogue's fp16 PReLU output");
+    return gemm_bf16<EPI_STORE_F32>(h, h->w16_mode, yb, h->fmt16 ? h->w.fc_w_h[0] : h->w.fc_w_bf, h->fmt16 ? h->w.fc_w_h[1] : h->w.fc_w_bl,
+                                   h->w.fc_b, mask, M, NSPK * D, D, true, st);
   }
   if ((rc = launch_prelu(h, a, h->w.prelu_a, y_scratch, M * D, st))) return rc;
   if ((rc = launch_round_tf32(h, y_scratch, M * D, st))) return rc;

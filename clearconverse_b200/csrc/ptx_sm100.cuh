@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace resep {
@@ -294,6 +295,34 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return r;
 }
 
+// ---------------------------------------------------------------- the two 16-bit operand formats of kind::f16
+// F16 = false: bf16 (8-bit mantissa; the throughput mode).  F16 = true: IEEE fp16 (11-bit significand, the precision
+// of tf32) -- the same kernels at the same speed carry the fp32-tolerance contract (max-abs <= 1e-3) when the
+// activations fit fp16's range, which LayerNorm'ed transformer activations do.
+template <bool F16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16> __device__ __forceinline__ float2 unpack16(uint32_t w) {
+  if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+// a . a + b . b accumulated in the packed 16-bit format (HFMA2): squared norms for the attention stabiliser
+template <bool F16> __device__ __forceinline__ uint32_t hfma2_sq(uint32_t v, uint32_t acc) {
+  if (F16) { const __half2 x = *reinterpret_cast<const __half2*>(&v); const __half2 r = __hfma2(x, x, *reinterpret_cast<const __half2*>(&acc)); return *reinterpret_cast<const uint32_t*>(&r); }
+  const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&v);
+  const __nv_bfloat162 r = __hfma2(x, x, *reinterpret_cast<const __nv_bfloat162*>(&acc));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
@@ -310,6 +339,26 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
   asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// the same three forms for either 16-bit format
+template <bool F16> __device__ __forceinline__ void mma16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16) asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16> __device__ __forceinline__ void mma16_16816_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16) asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+  else asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+template <bool F16> __device__ __forceinline__ void mma16_16816_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c01, float c23) {
+  if (F16) asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c01), "f"(c23));
+  else asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c01), "f"(c23));
 }
 
 // same with a zero accumulator input (the compiler then feeds RZ instead of zeroing four registers first)

@@ -2,6 +2,8 @@
 // plans, workspace carving and the forward-pass orchestration that restates
 // SepformerSeparation.separate_batch (speechbrain/inference/separation.py), called by the
 // reference at /root/reference/back/api.py:1077.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
@@ -59,6 +61,14 @@ struct ArenaBuilder {
     for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i] - __bfloat162float(__float2bfloat16_rn(src[i])));
     return add(tmp.data(), n * sizeof(bf16));
   }
+  size_t add_f16(const float* src, size_t n, bool lo) {   // IEEE fp16: fp16(W), or fp16(W - fp16(W))
+    std::vector<__half> tmp(n);
+    for (size_t i = 0; i < n; ++i) {
+      const __half hi = __float2half_rn(src[i]);
+      tmp[i] = lo ? __float2half_rn(src[i] - __half2float(hi)) : hi;
+    }
+    return add(tmp.data(), n * sizeof(__half));
+  }
   size_t add_bf16(const float* src, size_t n) {
     std::vector<bf16> tmp(n);
     for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
@@ -81,6 +91,10 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
     fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_bf16(src, n)});
     fixes.push_back({reinterpret_cast<const void**>(&slot_lo), ab.add_bf16_lo(src, n)});
   };
+  auto Hf = [&](const bf16* (&slot)[2], const float* src, size_t n) {
+    fixes.push_back({reinterpret_cast<const void**>(&slot[0]), ab.add_f16(src, n, false)});
+    fixes.push_back({reinterpret_cast<const void**>(&slot[1]), ab.add_f16(src, n, true)});
+  };
   auto Tf = [&](const float*& slot, const float*& slot_lo, const float* src, size_t n) {
     fixes.push_back({reinterpret_cast<const void**>(&slot), ab.add_tf32(src, n)});
     fixes.push_back({reinterpret_cast<const void**>(&slot_lo), ab.add_tf32_lo(src, n)});
@@ -92,6 +106,7 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   F(d.fc_b, w->fc_b, NSPK * D);
   F(d.pe, w->pe, (size_t)w->pe_rows * D);
   Bf(d.fc_w_bf, d.fc_w_bl, w->fc_w, NSPK * D * D);
+  Hf(d.fc_w_h, w->fc_w, NSPK * D * D);
   Tf(d.fc_w_tf, d.fc_w_lo, w->fc_w, NSPK * D * D);
   d.pe_rows = w->pe_rows;
   const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
@@ -136,12 +151,16 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
               pb[r_new] = s.in_proj_b[r_old] * sc;
             }
         Bf(t.in_w_bf, t.in_w_bl, pw.data(), 3 * D * D);
+        Hf(t.in_w_h, pw.data(), 3 * D * D);
         F(t.in_b_hi, pb.data(), 3 * D);
         std::memcpy(h->host_par.data() + (size_t)(b * NL + l) * POST_PAR + 4 * D + FFN, pb.data(), 3 * D * 4);
       }
       Bf(t.out_w_bf, t.out_w_bl, s.out_proj_w, D * D);
       Bf(t.f1_w_bf, t.f1_w_bl, s.ffn1_w, (size_t)FFN * D);
       Bf(t.f2_w_bf, t.f2_w_bl, s.ffn2_w, (size_t)D * FFN);
+      Hf(t.out_w_h, s.out_proj_w, D * D);
+      Hf(t.f1_w_h, s.ffn1_w, (size_t)FFN * D);
+      Hf(t.f2_w_h, s.ffn2_w, (size_t)D * FFN);
       Tf(t.in_w_tf, t.in_w_lo, s.in_proj_w, 3 * D * D);
       Tf(t.out_w_tf, t.out_w_lo, s.out_proj_w, D * D);
       Tf(t.f1_w_tf, t.f1_w_lo, s.ffn1_w, (size_t)FFN * D);
@@ -487,7 +506,12 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
                          cudaStream_t st, const ResepDebugOut* dbg, const ResepSpanCtl* span) {
   if (!h) return RESEP_EINVAL;
   if (!mix || !item_off || !item_len || !est || B <= 0) return set_err(h, RESEP_EINVAL, "null pointer or B <= 0");
-  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_FP16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  // RESEP_PREC_FP16 takes every code path of the bf16 mode: same kernels, instantiated for IEEE fp16 operands, with every
+  // weight as hi + lo
+  h->fmt16 = precision == RESEP_PREC_FP16;
+  h->w16_mode = h->fmt16 ? h->w16_mode_fp16 : h->w16_mode_bf16;
+  if (precision == RESEP_PREC_FP16) precision = RESEP_PREC_BF16;
   if (batch_mode != RESEP_BATCH_COUPLED && batch_mode != RESEP_BATCH_INDEPENDENT && !(span && batch_mode == RESEP_BATCH_SPAN_EXACT))
     return set_err(h, RESEP_EINVAL, "unknown batch_mode");
   // span != nullptr: one phase of a forward whose memory transformer runs elsewhere (resep_forward_span)
@@ -605,6 +629,8 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
     else if (!strcmp(m, "bf16x2")) h->w16_mode = 1;   // every weight as hi + lo
     else if (!strcmp(m, "mixed")) h->w16_mode = 2;    // default
   }
+  h->w16_mode_bf16 = h->w16_mode;
+  if (const char* m = getenv("RESEP_W16F")) h->w16_mode_fp16 = !strcmp(m, "mixed") ? 2 : !strcmp(m, "single") ? 0 : 1;
   if (const char* g = getenv("RESEP_GRAPH")) h->use_graphs = g[0] != '0';
   int rc = upload_weights(h, w);
   if (rc) {
@@ -739,7 +765,10 @@ int resep_memory_block(ResepHandle* h, const float* chunk_means, float* hc, int 
                        int precision, void* stream) {
   if (!h) return RESEP_EINVAL;
   if (!chunk_means || !hc || n_chunks <= 0) return set_err(h, RESEP_EINVAL, "null pointer or n_chunks <= 0");
-  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_FP16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  h->fmt16 = precision == RESEP_PREC_FP16;
+  h->w16_mode = h->fmt16 ? h->w16_mode_fp16 : h->w16_mode_bf16;
+  if (precision == RESEP_PREC_FP16) precision = RESEP_PREC_BF16;
   if (n_chunks > h->w.pe_rows) return set_err(h, RESEP_EPOS, "memory sequence longer than the positional-encoding table");
   RESEP_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -804,7 +833,10 @@ int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, i
   if (!h) return RESEP_EINVAL;
   if (!x || block < 0 || block > 2 || layer < 0 || layer >= NL || n_seq <= 0 || seq_len <= 0)
     return set_err(h, RESEP_EINVAL, "bad argument");
-  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_BF16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  if (precision < RESEP_PREC_FP32 || precision > RESEP_PREC_FP16) return set_err(h, RESEP_EINVAL, "unknown precision");
+  h->fmt16 = precision == RESEP_PREC_FP16;
+  h->w16_mode = h->fmt16 ? h->w16_mode_fp16 : h->w16_mode_bf16;
+  if (precision == RESEP_PREC_FP16) precision = RESEP_PREC_BF16;
   RESEP_CUDA(h, cudaSetDevice(h->device));
   const int64_t rows = (int64_t)n_seq * seq_len;
   Workspace ws = carve(workspace, rows, 0);

@@ -39,6 +39,9 @@ struct LayerDev {
   const bf16 *in_w_bf, *out_w_bf, *f1_w_bf, *f2_w_bf;       // bf16 copies (RESEP_PREC_BF16); in_w_bf / in_w_bl rows head-interleaved
   const float* in_b_hi;                                     // in_b in the same head-interleaved order
   const bf16 *in_w_bl, *out_w_bl, *f1_w_bl, *f2_w_bl;       // bf16(W - bf16(W)): low part for the split-weight mode
+  // the same four weights as IEEE fp16 hi + lo (RESEP_PREC_FP16; stored behind the 16-bit container type `bf16`):
+  // [0] = fp16(W), [1] = fp16(W - fp16(W)); in_w rows head-interleaved and key rows pre-scaled like in_w_bf
+  const bf16 *in_w_h[2], *out_w_h[2], *f1_w_h[2], *f2_w_h[2];
   const float *in_w_tf, *out_w_tf, *f1_w_tf, *f2_w_tf;      // tf32-rounded fp32 copies (RESEP_PREC_TF32): hi part
   const float *in_w_lo, *out_w_lo, *f1_w_lo, *f2_w_lo;      // tf32(W - hi): the TF32 mode runs W = hi + lo
   // HOST copy of out_b[128], norm2_w[128], norm2_b[128], f2_b[128], f1_b[1024]: k_post2_tc takes them as kernel
@@ -53,6 +56,7 @@ struct BlockDev {
 struct WeightsDev {
   const float *enc_w, *dec_w, *prelu_a, *fc_w, *fc_b, *pe;
   const bf16 *fc_w_bf, *fc_w_bl;
+  const bf16* fc_w_h[2];    // fp16 hi / lo
   const float *fc_w_tf, *fc_w_lo;
   int64_t pe_rows;
   BlockDev blk[3];  // 0 = seg_model[0], 1 = seg_model[1], 2 = mem_model[0]
@@ -108,6 +112,11 @@ struct ResepHandle {
   // RESEP_PREC_BF16 weight operands (DESIGN.md "precision modes"): 2 = in-proj / out-proj / output_fc as bf16 hi + lo
   // (two MMAs per K-slice), FFN weights as one rounded bf16 (default); 1 = every weight hi + lo; 0 = bf16(W) only
   int w16_mode = 2;
+  // what the 16-bit kernels of the CURRENT call compute in: 0 = bf16 (RESEP_PREC_BF16), 1 = fp16 (RESEP_PREC_FP16, every
+  // weight hi + lo).  Set by the forward entry points from the precision argument.
+  int fmt16 = 0;
+  int w16_mode_fp16 = 1;    // the fp16 mode's setting: every weight hi + lo (RESEP_W16F=mixed: FFN weights single fp16)
+  int w16_mode_bf16 = 2;    // the bf16 mode's weight-operand setting (RESEP_W16), restored when a bf16 call follows an fp16 one
   bool prof_on = false;   // resep_profile(): bracket every launch with CUDA events
   struct ProfRec { cudaEvent_t a, b; const char* name; };
   std::vector<ProfRec> prof;

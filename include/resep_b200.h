@@ -45,6 +45,9 @@ extern "C" {
 #define RESEP_PREC_FP32     0   /* fp32 FMA kernels (no tensor cores): reference-grade parity path  */
 #define RESEP_PREC_TF32     1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM                      */
 #define RESEP_PREC_BF16     2   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM       */
+#define RESEP_PREC_FP16     3   /* the same fused kernels with IEEE fp16 operands (11-bit significand
+                                   = tf32's precision), every weight as fp16 hi + lo: the fast
+                                   fp32-tolerance mode (max-abs <= 1e-3)                            */
 
 /* batch semantics of the memory (inter-chunk) transformer, SURVEY.md section 8e */
 #define RESEP_BATCH_COUPLED      0  /* upstream's literal B>1 behaviour: chunks of all items form ONE

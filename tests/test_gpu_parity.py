@@ -234,9 +234,13 @@ def test_tc_linear_matches_fp32_kernel(sep_fp32):
         assert torch.equal(outs[2], outs[4])                                       # test code 4 == the default mode
 
 
+@pytest.mark.parametrize("prec", ["tf32", "fp16"])
 @pytest.mark.parametrize("B,T,seed", [(1, 100, 5), (2, 2000, 2), (1, 32000, 1), (3, 9000, 5)])
-def test_tf32_forward_within_spec(make_sep, oracle, B, T, seed):
-    sep = make_sep("tf32", "coupled")
+def test_tf32_forward_within_spec(make_sep, oracle, B, T, seed, prec):
+    """The fp32-tolerance contract (max-abs <= 1e-3) for both tensor-core modes that carry it: "tf32" (kind::tf32
+    GEMMs, unfused) and "fp16" (the fused bf16-mode kernels instantiated for IEEE fp16 operands -- 11-bit significand
+    like tf32 -- with every weight as fp16 hi + lo)."""
+    sep = make_sep(prec, "coupled")
     mix = synth_batch(B, T, seed)
     want = oracle.separate_batch(mix)
     got = sep.separate_batch(mix).cpu()
@@ -274,14 +278,14 @@ def test_config2_full_size_all_modes(make_sep, oracle):
     """configs[1]: 16 x 4 s.  The oracle runs the whole batch (about 10 s of CPU)."""
     mix = synth_batch(16, 32000, 2)
     want = oracle.separate_batch(mix)
-    for prec, tol in (("fp32", TOL_FP32), ("tf32", TOL_SPEC)):
+    for prec, tol in (("fp32", TOL_FP32), ("tf32", TOL_SPEC), ("fp16", TOL_SPEC)):
         got = make_sep(prec, "coupled").separate_batch(mix).cpu()
         assert (got - want).abs().max().item() <= tol, prec
     got = make_sep("bf16", "coupled").separate_batch(mix).cpu()
     assert_bf16_gates(got, want, mix, unmasked=True, tag="config 2 coupled")
     # the product-faithful semantics at the same size: per-item memory sequences == 16 oracle calls with B = 1
     want_ind = torch.cat([oracle.separate_batch(mix[i:i + 1]) for i in range(16)])
-    for prec, tol in (("fp32", TOL_FP32), ("tf32", TOL_SPEC)):
+    for prec, tol in (("fp32", TOL_FP32), ("tf32", TOL_SPEC), ("fp16", TOL_SPEC)):
         got = make_sep(prec, "independent").separate_batch(mix).cpu()
         assert (got - want_ind).abs().max().item() <= tol, prec
     got = make_sep("bf16", "independent").separate_batch(mix).cpu()
@@ -301,6 +305,8 @@ def test_config3_long_sequence_properties(make_sep, oracle):
     assert (got.cpu() - want).abs().max().item() <= TOL_FP32
     tf = make_sep("tf32", "coupled").separate_batch(mix).cpu()
     assert (tf - want).abs().max().item() <= TOL_SPEC
+    hf = make_sep("fp16", "coupled").separate_batch(mix).cpu()
+    assert (hf - want).abs().max().item() <= TOL_SPEC
     # the bf16 budget "must be re-checked at 60 s" (400 chunks through the memory transformer)
     bf = make_sep("bf16", "coupled").separate_batch(mix).cpu()
     assert_bf16_gates(bf, want, mix, unmasked=True, tag="config 3")
@@ -637,7 +643,7 @@ def test_from_hparams_end_to_end_like_api_py(tmp_path, oracle, sds):
             sd = torch.load(tmp_path / f"{name}.ckpt", weights_only=True)
             twin.mods[name].load_state_dict({k: v for k, v in sd.items() if not k.endswith("pos_enc.pe")})
         want = twin.separate_batch(subsegment.cpu())
-        assert separator.precision == "tf32"                                     # the package default: the 1e-3 contract
+        assert separator.precision == "fp16"                                     # the package default: the 1e-3 contract
         assert (separated.cpu() - want).abs().max().item() <= TOL_SPEC
         assert (separated.cpu() - oracle.separate_batch(subsegment.cpu())).abs().max().item() > 1e-2   # really these files' weights
         assert separator.hparams.num_spks == 2 and separator.hparams.sample_rate == 8000
@@ -673,7 +679,7 @@ def test_separate_file_like_upstream(tmp_path, make_sep):
     assert got16.shape == want16.shape and (got16 - want16).abs().max().item() <= 1e-4
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tf32", 2e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tf32", 2e-3), ("fp16", 2e-3), ("bf16", 5e-2)])
 @pytest.mark.parametrize("block,layer,n_seq,seq_len", [(0, 0, 5, 150), (1, 7, 3, 150), (2, 3, 1, 40), (2, 0, 1, 432)])
 def test_layer_entry_point_matches_oracle_layer(make_sep, oracle, prec, tol, block, layer, n_seq, seq_len):
     """``resep_layer_fwd`` (per-kernel entry point of the C ABI): one pre-norm TransformerEncoderLayer on [n_seq,
@@ -693,7 +699,7 @@ def test_layer_entry_point_matches_oracle_layer(make_sep, oracle, prec, tol, blo
     assert eng.lib.resep_workspace_bytes(eng.handle, 1, lens, 0, C.byref(need)) == 0
     ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
     rc = eng.lib.resep_layer_fwd(eng.handle, block, layer, d_x.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(),
-                                 {"fp32": 0, "tf32": 1, "bf16": 2}[prec], C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                 {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}[prec], C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, eng.lib.resep_last_error(eng.handle)
     torch.cuda.synchronize()
     got = d_x.cpu().view(n_seq, seq_len, 128)
@@ -795,3 +801,33 @@ def test_tcgen05_attention_against_the_mma_sync_kernel(cuda_lib_built):
                 assert torch.isfinite(got).all(), (scale, n_seq)
                 err = (got - want).double().pow(2).sum().sqrt() / want.double().pow(2).sum().sqrt()
                 assert -20 * torch.log10(err).item() > min_db, (scale, n_seq, err.item())
+
+
+def test_fp16_mode_other_weight_seeds_ragged_and_invariant(cuda_lib_built):
+    """The fp16 mode (fast fp32-tolerance path) beyond the module-wide weights: three more weight seeds, a ragged
+    independent batch against per-segment oracle calls, batch-composition invariance bit for bit, and the same bits
+    from the pipelined two-lane driver."""
+    from clearconverse_b200 import SepformerSeparation
+    from oracle.resepformer_oracle import OracleSepformerSeparation
+    for wseed in (1, 2, 3):
+        oracle = OracleSepformerSeparation(seed=wseed)
+        with SepformerSeparation(oracle.component_state_dicts(), device="cuda:0", precision="fp16", batch_mode="coupled") as sep:
+            for mix in (synth_batch(2, 2000, 2), synth_batch(3, 9000, 5), synth_batch(1, 32000, 1)):
+                got = sep.separate_batch(mix).cpu()
+                assert (got - oracle.separate_batch(mix)).abs().max().item() <= TOL_SPEC, wseed
+    oracle = OracleSepformerSeparation(seed=0)
+    with SepformerSeparation(oracle.component_state_dicts(), device="cuda:0", precision="fp16", batch_mode="independent") as sep:
+        lens = [4000, 16, 9000, 1211, 32000, 2500, 1200, 2408]
+        segs = [synth_mixture(n, 70 + i)[0] for i, n in enumerate(lens)]
+        outs = sep.separate_segments(segs)
+        for s_, o in zip(segs, outs):
+            assert (o.cpu() - oracle.separate_batch(s_[None])[0]).abs().max().item() <= TOL_SPEC, s_.numel()
+        alone = [sep.separate_segments([s_])[0] for s_ in segs]
+        rev = sep.separate_segments(segs[::-1])[::-1]
+        for a, b, c in zip(outs, alone, rev):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        groups = [[s_.cuda() for s_ in segs[0:3]], [s_.cuda() for s_ in segs[3:8]]]
+        want = [sep.separate_segments(g) for g in groups]
+        got = list(sep.separate_stream(iter(groups), depth=2))
+        for g_, w_ in zip(got, want):
+            assert all(torch.equal(x, y) for x, y in zip(g_, w_))
