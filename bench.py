@@ -243,6 +243,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-blocks", action="store_true",
+                    help="skip the sustained / meeting / long_split / latency / cpu_baseline blocks (the ncu passes under "
+                         "profiles/ use this: the timed step and its kernels are the same, the run is ~100x shorter)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -353,8 +356,34 @@ def main():
         dist.all_reduce(e2e_serial_s, op=dist.ReduceOp.MAX)
     e2e_serial_value = audio_s / e2e_serial_s.item()
 
+    # ---------------- host <-> device copy rates with EVERY rank copying at the same time (the e2e path's only shared
+    # resource: PCIe root complexes / host memory; there is no data-path collective).  Compared across N this names
+    # what the e2e scaling loses.
+    copy_probe = None
+    if not args.no_side_blocks:
+        barrier()
+        cp_s = torch.cuda.Stream(dev)
+        n_cp = 200
+        with torch.cuda.stream(cp_s):
+            ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ea.record(cp_s)
+            for i in range(n_cp):
+                mix.copy_(host_ins[i & 1], non_blocking=True)
+            eb.record(cp_s)
+            for i in range(n_cp):
+                host_outs[i % 3].view(-1)[:BATCH * T * 2].copy_(flush[:BATCH * T * 2 * 4].view(torch.float32), non_blocking=True)
+            ec.record(cp_s)
+        cp_s.synchronize()
+        t = torch.tensor([ea.elapsed_time(eb), eb.elapsed_time(ec)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_probe = {"h2d_gbs_per_gpu": n_cp * BATCH * T * 4 / (t[0].item() / 1e3) / 1e9,
+                      "d2h_gbs_per_gpu": n_cp * BATCH * T * 2 * 4 / (t[1].item() / 1e3) / 1e9,
+                      "note": f"{n_cp} x the step's 2.0 MB input H2D, then {n_cp} x its 4.1 MB result D2H, pinned host memory, all {world} ranks at once (slowest rank)",
+                      "needed_gbs_per_gpu_at_value": (BATCH * T * 4 + BATCH * T * 2 * 4) / (total_s / args.steps) / 1e9}
+
     # ---------------- sustained: the same step through the same driver for >= 3 s (clocks and power sampled throughout)
-    sust_steps = max(args.steps, int(3.2 / max(total_s / args.steps, 1e-6)))
+    sust_steps = max(args.steps, int(3.2 / max(total_s / args.steps, 1e-6))) if not args.no_side_blocks else args.steps
     barrier()
     ev0s, ev1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks_s:
@@ -372,8 +401,8 @@ def main():
                  "reasons": cs["reasons"]}
 
     # ---------------- BASELINE configs[3]: the synthetic 1-hour meeting, sharded over the N GPUs (strong scaling)
-    meeting = run_meeting(sds, args.precision, rank, world, dev, dist, barrier)
-    long_split = run_long_split(sep, rank, world, dev, dist) if world > 1 else None
+    meeting = run_meeting(sds, args.precision, rank, world, dev, dist, barrier) if not args.no_side_blocks else None
+    long_split = run_long_split(sep, rank, world, dev, dist) if world > 1 and not args.no_side_blocks else None
 
     if rank != 0:
         if world > 1:
@@ -389,13 +418,15 @@ def main():
             sep.separate_batch(mixes[i % len(mixes)])
             torch.cuda.current_stream().synchronize()
         return 1e3 * (time.perf_counter() - t0) / reps
-    same = [synth.synth_batch(1, T, 5).to(dev)]
-    one_call_ms(same, 5)
-    distinct = [synth.synth_batch(1, T - 801 * i, 60 + i).to(dev) for i in range(32)]        # 4 s ... 0.9 s, every length new
-    latency = {"b1_4s_repeated_shape_ms": one_call_ms(same, 50),
-               "b1_first_sighting_of_each_length_ms": one_call_ms(distinct, 32),              # plan upload + eager launches
-               "b1_distinct_lengths_seen_before_ms": one_call_ms(distinct, 64),               # plans cached; graphs after the 2nd sighting
-               "note": "blocking separate_batch on a device-resident [1,T] mixture, host wall clock per call"}
+    latency = None
+    if not args.no_side_blocks:
+        same = [synth.synth_batch(1, T, 5).to(dev)]
+        one_call_ms(same, 5)
+        distinct = [synth.synth_batch(1, T - 801 * i, 60 + i).to(dev) for i in range(32)]        # 4 s ... 0.9 s, every length new
+        latency = {"b1_4s_repeated_shape_ms": one_call_ms(same, 50),
+                   "b1_first_sighting_of_each_length_ms": one_call_ms(distinct, 32),              # plan upload + eager launches
+                   "b1_distinct_lengths_seen_before_ms": one_call_ms(distinct, 64),               # plans cached; graphs after the 2nd sighting
+                   "note": "blocking separate_batch on a device-resident [1,T] mixture, host wall clock per call"}
 
     # ---------------- roofline of the dominant kernel (separate pass; events around every launch)
     pk = peaks()
@@ -453,7 +484,7 @@ def main():
 
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and not args.no_side_blocks and world == 1:
         v, times, threads = time_oracle(sds, items=BATCH, reps=5)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"the whole step (B={BATCH} x {SECONDS} s, coupled), oracle fp32 eager PyTorch, 1 warm-up + median of 5 "
@@ -475,6 +506,7 @@ def main():
                            "note": "one forward at a time on one stream, per-step CUDA events, L2 flushed between steps"},
         "clocks": clocks.summary(),
         "sustained": sustained,
+        "copy_probe": copy_probe,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * T * 4, "d2h_bytes_per_step": BATCH * T * 2 * 4,
                 "api": "SepformerSeparation.separate_stream (pinned host batches in, pinned host results out, copies overlapped, two forwards in flight)",
                 "serial_value": e2e_serial_value, "serial_api": "separate_batch(host) + blocking copy per step"},

@@ -28,17 +28,21 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Encoder.  One CTA = 30 consecutive rows of one chunk (5 CTAs per chunk), one thread per
-// filter.  The 248 samples the rows need are staged in shared memory once; each thread keeps
-// its 16 taps in registers; stores are 512 B contiguous per row.  Rows past the item's last
-// frame (the `rest` zero padding of _padfeature) are written as zeros.
+// Encoder (dual_path.Encoder: relu(conv1d k16 s8), no bias) writing token-major, chunk-padded rows.  One CTA = 30
+// consecutive rows of one chunk (5 CTAs per chunk); a WARP produces a row: lane l holds the 16 taps of filters
+// 4 l .. 4 l + 3 in registers, reads the row's 16 samples as four broadcast 16-byte loads from the staged window and
+// stores one float4 -- a 512-byte row per store instruction.  Rows past the item's last frame (the `rest` zero padding
+// of _padfeature) are written as zeros.  With `o` != null the first transformer block's prologue is fused in:
+// o = x0 + pe[frame in chunk] (hc is zero for the first block, so its skip input is x0 itself): the separate
+// k_block_prologue pass over the same 33 MB (config 2) disappears.
 constexpr int ENC_ROWS = 30;
 __global__ void __launch_bounds__(D) k_encoder_chunked(const float* __restrict__ mix, const float* __restrict__ enc_w,
                                                        const int64_t* __restrict__ item_off,
                                                        const int64_t* __restrict__ item_len,
                                                        const int* __restrict__ item_L, const int* __restrict__ chunk_item,
-                                                       const int* __restrict__ chunk_frame0, float* __restrict__ x0) {
-  __shared__ float s[ENC_ROWS * STRIDE + KSZ];
+                                                       const int* __restrict__ chunk_frame0, float* __restrict__ x0,
+                                                       float* __restrict__ o, const float* __restrict__ pe) {
+  __shared__ __align__(16) float s[ENC_ROWS * STRIDE + KSZ];
   const int chunk = blockIdx.x / (CHUNK / ENC_ROWS);
   const int r0 = (blockIdx.x % (CHUNK / ENC_ROWS)) * ENC_ROWS;
   const int item = chunk_item[chunk];
@@ -46,32 +50,51 @@ __global__ void __launch_bounds__(D) k_encoder_chunked(const float* __restrict__
   const int L = item_L[item];
   const int64_t T = item_len[item];
   const float* src = mix + item_off[item];
-  const int n = threadIdx.x;
-  for (int i = n; i < ENC_ROWS * STRIDE + KSZ - STRIDE; i += D) {
-    int64_t t = (int64_t)frame0 * STRIDE + i;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < ENC_ROWS * STRIDE + KSZ; i += D) {
+    const int64_t t = (int64_t)frame0 * STRIDE + i;
     s[i] = (t < T) ? src[t] : 0.f;
   }
-  float w[KSZ];
+  float w[4][KSZ];
 #pragma unroll
-  for (int k = 0; k < KSZ; ++k) w[k] = enc_w[n * KSZ + k];
-  __syncthreads();
-  float* dst = x0 + ((int64_t)chunk * CHUNK + r0) * D + n;
-#pragma unroll 2
-  for (int j = 0; j < ENC_ROWS; ++j) {
-    float acc = 0.f;
-    if (frame0 + j < L) {
+  for (int f = 0; f < 4; ++f)
 #pragma unroll
-      for (int k = 0; k < KSZ; ++k) acc = fmaf(w[k], s[j * STRIDE + k], acc);
-      acc = fmaxf(acc, 0.f);
+    for (int k = 0; k < KSZ; k += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(enc_w + (4 * lane + f) * KSZ + k);
+      w[f][k] = t4.x; w[f][k + 1] = t4.y; w[f][k + 2] = t4.z; w[f][k + 3] = t4.w;
     }
-    dst[(int64_t)j * D] = acc;
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(x0 + ((int64_t)chunk * CHUNK + r0) * D) + lane;
+  float4* dsto = o != nullptr ? reinterpret_cast<float4*>(o + ((int64_t)chunk * CHUNK + r0) * D) + lane : nullptr;
+  const float4* pe4 = reinterpret_cast<const float4*>(pe + (int64_t)r0 * D) + lane;       // position in the chunk = row in the chunk
+  for (int j = warp; j < ENC_ROWS; j += D / 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (frame0 + j < L) {
+      float x[KSZ];
+#pragma unroll
+      for (int k = 0; k < KSZ; k += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&s[j * STRIDE + k]);
+        x[k] = t4.x; x[k + 1] = t4.y; x[k + 2] = t4.z; x[k + 3] = t4.w;
+      }
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+#pragma unroll
+        for (int k = 0; k < KSZ; ++k) acc[f] = fmaf(w[f][k], x[k], acc[f]);     // same order as the one-filter-per-thread form
+        acc[f] = fmaxf(acc[f], 0.f);
+      }
+    }
+    dst[(int64_t)j * (D / 4)] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (dsto != nullptr) {
+      const float4 e = pe4[(int64_t)j * (D / 4)];
+      dsto[(int64_t)j * (D / 4)] = make_float4(acc[0] + e.x, acc[1] + e.y, acc[2] + e.z, acc[3] + e.w);
+    }
   }
 }
 
-int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st) {
+int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st, float* o_fused) {
   ProfScope prof_scope_69(h, "k_encoder_chunked", st);
   k_encoder_chunked<<<(unsigned)(p.n_chunks * (CHUNK / ENC_ROWS)), D, 0, st>>>(
-      mix, h->w.enc_w, p.d_item_off, p.d_item_len, p.d_item_L, p.d_chunk_item, p.d_chunk_frame0, x0);
+      mix, h->w.enc_w, p.d_item_off, p.d_item_len, p.d_item_L, p.d_chunk_item, p.d_chunk_frame0, x0, o_fused, h->w.pe);
   RESEP_LAUNCH_CHECK(h, "k_encoder_chunked");
   return RESEP_OK;
 }

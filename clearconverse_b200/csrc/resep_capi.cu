@@ -410,10 +410,10 @@ static int run_layer(ResepHandle* h, const LayerDev& lw, float* o, const SeqDesc
 
 static int run_block(ResepHandle* h, int blk, const float* xprev, const float* hc, float* xin, float* o, float* out,
                      float* seq_mean, const SeqDesc& sd, const Workspace& ws, int precision, cudaStream_t st,
-                     bf16* prelu_out = nullptr) {
+                     bf16* prelu_out = nullptr, bool prologue_done = false) {
   int rc;
   const BlockDev& bw = h->w.blk[blk];
-  if ((rc = launch_block_prologue(h, xprev, hc, xin, o, sd.rows, sd.pos, sd.seq_len, st))) return rc;
+  if (!prologue_done && (rc = launch_block_prologue(h, xprev, hc, xin, o, sd.rows, sd.pos, sd.seq_len, st))) return rc;
   for (int l = 0; l < NL; ++l)
     if ((rc = run_layer(h, bw.layers[l], o, sd, ws, precision, st))) return rc;
   return launch_block_epilogue(h, o, bw.fn_w, bw.fn_b, bw.gln_w, bw.gln_b, xin, out, seq_mean, sd.n_seq, sd.seq_len,
@@ -525,7 +525,12 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
     return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
   if (precision != RESEP_PREC_FP32 && (rc = tc_init(h))) return rc;
 
-  if (!phase2 && (rc = launch_encoder_chunked(h, mix, *p, ws.x0, st))) return rc;
+  // The encoder also writes the first block's o = x0 + pe when that block runs as ONE slice (a sliced block re-uses the
+  // same o scratch for every slice, so its prologue stays per slice).
+  static const int64_t slice_env0 = getenv("RESEP_SLICE_CHUNKS") ? atoll(getenv("RESEP_SLICE_CHUNKS")) : 378;
+  static const bool fuse_env = !(getenv("RESEP_ENC_FUSE") && getenv("RESEP_ENC_FUSE")[0] == '0');
+  const bool enc_fused = fuse_env && !phase2 && (p->n_chunks <= 512 || slice_env0 <= 0);
+  if (!phase2 && (rc = launch_encoder_chunked(h, mix, *p, ws.x0, st, enc_fused ? ws.o : nullptr))) return rc;
   if (dbg && dbg->enc) RESEP_CUDA(h, cudaMemcpyAsync(dbg->enc, ws.x0, p->M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   SeqDesc intra{p->M, (int)p->n_chunks, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK};
@@ -542,18 +547,18 @@ static int forward_eager(ResepHandle* h, const float* mix, const int64_t* item_o
   static const int64_t slice_env = getenv("RESEP_SLICE_CHUNKS") ? atoll(getenv("RESEP_SLICE_CHUNKS")) : 378;
   const int64_t slice = (p->n_chunks <= 512 || slice_env <= 0) ? p->n_chunks : slice_env;
   auto run_intra = [&](int blk, const float* xprev, const float* hc, float* xin, float* out, float* seq_mean,
-                       bf16* prelu_out_) -> int {
+                       bf16* prelu_out_, bool prologue_done = false) -> int {
     for (int64_t c0 = 0; c0 < p->n_chunks; c0 += slice) {
       const int64_t nc = std::min<int64_t>(slice, p->n_chunks - c0), r0 = c0 * CHUNK * D;
       SeqDesc sl{nc * CHUNK, (int)nc, CHUNK, nullptr, nullptr, nullptr, nullptr, 0, CHUNK, true};
       int rc2 = run_block(h, blk, xprev + r0, hc ? hc + c0 * D : nullptr, xin + r0, ws.o, out + r0,
-                          seq_mean ? seq_mean + c0 * D : nullptr, sl, ws, precision, st, prelu_out_ ? prelu_out_ + r0 : nullptr);
+                          seq_mean ? seq_mean + c0 * D : nullptr, sl, ws, precision, st, prelu_out_ ? prelu_out_ + r0 : nullptr, prologue_done);
       if (rc2) return rc2;
     }
     return RESEP_OK;
   };
   // seg_model[0](x + 0): skip input is the encoder output itself
-  if (!phase2 && (rc = run_intra(0, ws.x0, nullptr, ws.x0, ws.a, ws.hc_in, nullptr))) return rc;
+  if (!phase2 && (rc = run_intra(0, ws.x0, nullptr, ws.x0, ws.a, ws.hc_in, nullptr, enc_fused))) return rc;
   if (phase1) {
     RESEP_CUDA(h, cudaMemcpyAsync(span->chunk_means, ws.hc_in, p->n_chunks * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return RESEP_OK;

@@ -176,7 +176,8 @@ struct ProfScope {
   } while (0)
 
 // ---------------------------------------------------------------- fp32 kernels (kernels_simt.cu)
-int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st);
+// o_fused != null: also writes o = x0 + pe[row in chunk], the prologue of the first transformer block
+int launch_encoder_chunked(ResepHandle* h, const float* mix, const Plan& p, float* x0, cudaStream_t st, float* o_fused = nullptr);
 int launch_encoder_single(ResepHandle* h, const float* mix, int64_t T, float* tokens, cudaStream_t st);
 // o = xin + pe[pos]; if hc != null first xin = xprev + hc[row / rows_per_hc] (written to xin)
 int launch_block_prologue(ResepHandle* h, const float* xprev, const float* hc, float* xin, float* o, int64_t rows,
