@@ -87,15 +87,46 @@ def assign_to_ranks(batches: list[Batch], world_size: int) -> list[list[int]]:
     return out
 
 
-def plan_shards(lens: list[int], world_size: int, max_chunks_per_batch: int = 2048, batches_per_rank: int = 4):
-    """(batches, per-rank batch indices).  With more than one rank the batch budget is lowered to
-    about total/(world_size * batches_per_rank) chunks so the greedy deal can balance the ranks."""
-    budget = max_chunks_per_batch
-    if world_size > 1:
-        total_chunks = sum(chunks_of(t) for t in lens)
-        budget = max(1, min(budget, -(-total_chunks // (world_size * batches_per_rank))))
-    batches = bucket_segments(lens, budget)
-    return batches, assign_to_ranks(batches, world_size)
+def plan_shards(lens: list[int], world_size: int, max_chunks_per_batch: int = 2048, batches_per_rank: int = 2):
+    """(batches, per-rank batch indices).  One rank: length-bucketed batches under the chunk budget.  Several ranks: the
+    SEGMENTS are dealt to the ranks first (longest-processing-time greedy on algorithmic FLOPs: the loads differ by at
+    most one short segment), then each rank's share is bucketed into ``batches_per_rank`` batches (two: one per lane of
+    the pipelined driver -- every batch pays the memory transformer's fixed latency, so fewer and larger is faster;
+    measured at 8 GPUs on the 1-hour meeting: 4.2 ms with five batches per rank)."""
+    if world_size <= 1:
+        batches = bucket_segments(lens, max_chunks_per_batch)
+        return batches, [list(range(len(batches)))]
+    load = [0] * world_size
+    mine: list[list[int]] = [[] for _ in range(world_size)]
+    for i in sorted(range(len(lens)), key=lambda j: (flops_of(lens[j]), -j), reverse=True):
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        mine[r].append(i)
+        load[r] += flops_of(lens[i])
+    batches: list[Batch] = []
+    per_rank: list[list[int]] = [[] for _ in range(world_size)]
+    for r in range(world_size):
+        if not mine[r]:
+            continue
+        chunks = sum(chunks_of(lens[i]) for i in mine[r])
+        k = max(batches_per_rank, -(-chunks // max_chunks_per_batch))     # more batches only if the chunk budget demands it
+        order = sorted(mine[r], key=lambda i: (chunks_of(lens[i]), lens[i], i), reverse=True)   # similar lengths together
+        while True:
+            target = chunks / k
+            cuts: list[Batch] = [Batch() for _ in range(k)]
+            seen = 0
+            for i in order:
+                c = chunks_of(lens[i])
+                b = cuts[min(k - 1, int((seen + c / 2) / target))]      # the batch the segment's midpoint falls into
+                b.indices.append(i); b.lens.append(lens[i]); b.chunks += c; b.flops += flops_of(lens[i])
+                seen += c
+            if all(b.chunks <= max_chunks_per_batch or len(b.indices) <= 1 for b in cuts) or k >= len(order):
+                break
+            k += 1                                                      # a batch came out over the workspace budget
+        for b in cuts:
+            if b.indices:
+                per_rank[r].append(len(batches))
+                batches.append(b)
+    return batches, per_rank
 
 
 class SharedResults:

@@ -41,7 +41,7 @@ mix60 = synth.synth_batch(1, 480000, seed=3).to(dev)
 ms = timed(lambda: sep.separate_batch(mix60), reps=10)
 out["config3_1x60s"] = {"ms": round(ms, 3), "audio_s_per_s": round(60 / (ms / 1e3), 1)}
 print(out["config3_1x60s"], flush=True)
-for prec in ("tf32", "fp32"):
+for prec in ("fp16", "tf32", "fp32"):
     s2 = SepformerSeparation(sds, device=dev, precision=prec, batch_mode="coupled")
     mix = synth.synth_batch(16, 32000, seed=2).to(dev)
     ms = timed(lambda: s2.separate_batch(mix), reps=3, warm=2)
@@ -70,4 +70,4 @@ out["config4_meeting_1gpu"] = {"segments": len(lens), "audio_s": round(sum(lens)
                                "note": "device-resident segments, host-side bucketing + launches inside the timed region"}
 print(out["config4_meeting_1gpu"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/configs_r1.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/configs_r2.json", "w"), indent=1)
