@@ -110,7 +110,7 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
   Tf(d.fc_w_tf, d.fc_w_lo, w->fc_w, NSPK * D * D);
   d.pe_rows = w->pe_rows;
   const ResepBlockWeights* src_blocks[3] = {&w->seg[0], &w->seg[1], &w->mem[0]};
-  constexpr size_t POST_PAR = 4 * D + FFN + 3 * D + 2 * D;
+  constexpr size_t POST_PAR = 4 * D + FFN + 3 * D + 2 * D + FFN;
   h->host_par.assign(3 * NL * POST_PAR, 0.f);
   for (int b = 0; b < 3; ++b) {
     const ResepBlockWeights& sb = *src_blocks[b];
@@ -160,6 +160,21 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
       Bf(t.f2_w_bf, t.f2_w_bl, s.ffn2_w, (size_t)D * FFN);
       Hf(t.out_w_h, s.out_proj_w, D * D);
       Hf(t.f1_w_h, s.ffn1_w, (size_t)FFN * D);
+      {  // norm2 folded into FFN1 for k_post2_tc (see LayerDev::f1g_w_bf)
+        std::vector<float> wg((size_t)FFN * D);
+        float* b1g = h->host_par.data() + (size_t)(b * NL + l) * POST_PAR + 9 * D + FFN;
+        for (int hh = 0; hh < FFN; ++hh) {
+          double acc = s.ffn1_b[hh];
+          for (int k = 0; k < D; ++k) {
+            wg[(size_t)hh * D + k] = s.ffn1_w[(size_t)hh * D + k] * s.norm2_w[k];
+            acc += (double)s.ffn1_w[(size_t)hh * D + k] * s.norm2_b[k];
+          }
+          b1g[hh] = (float)acc;
+        }
+        t.h_b1g = b1g;
+        Bf(t.f1g_w_bf, t.f1g_w_bl, wg.data(), (size_t)FFN * D);
+        Hf(t.f1g_w_h, wg.data(), (size_t)FFN * D);
+      }
       Hf(t.f2_w_h, s.ffn2_w, (size_t)D * FFN);
       Tf(t.in_w_tf, t.in_w_lo, s.in_proj_w, 3 * D * D);
       Tf(t.out_w_tf, t.out_w_lo, s.out_proj_w, D * D);

@@ -48,6 +48,11 @@ struct LayerDev {
   // parameters (constant bank) so that its epilogues do not spend shared-memory bandwidth on broadcast loads
   const float* h_post_par;
   const float* h_in_b;      // HOST copy of in_b_hi[384], norm1_w[128], norm1_b[128] (k_qkv2_tc kernel parameters)
+  // k_post2_tc's FFN1 with norm2's scale and shift folded in: W1g[h][k] = W1[h][k] * g2[k], b1g = b1 + W1 . be2, so
+  // that its LayerNorm epilogue only normalises (no parameter loads on the tile-boundary critical path).
+  // bf16 hi / lo, fp16 hi / lo, and the HOST copy of b1g[1024]
+  const bf16 *f1g_w_bf, *f1g_w_bl, *f1g_w_h[2];
+  const float* h_b1g;
 };
 struct BlockDev {
   LayerDev layers[NL];
