@@ -429,6 +429,47 @@ def main():
                    "note": "blocking separate_batch on a device-resident [1,T] mixture, host wall clock per call"}
 
     # ---------------- roofline of the dominant kernel (separate pass; events around every launch)
+    def layer_kernel_us():
+        """The three kernels of one intra layer at the bench shape, each launched 32 times back to back between two
+        events (no per-launch event records, no host gaps; no PDL: a launch includes its own set-up and tail), and the
+        whole layer 64 times back to back with PDL as in the product path.  Median of 5."""
+        import ctypes as C
+        from clearconverse_b200._lib import PRECISIONS
+        eng = sep._engine
+        code = PRECISIONS[args.precision]
+        n_chunks = shapes(BATCH, T)[2]
+        lens = (C.c_int64 * BATCH)(*[T] * BATCH)
+        need = C.c_size_t()
+        eng.lib.resep_workspace_bytes(eng.handle, BATCH, lens, code, C.byref(need))
+        wsb = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        x = torch.randn(n_chunks * 150, 128, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        def layer(n):
+            for _ in range(n):
+                assert eng.lib.resep_layer_fwd(eng.handle, 0, 1, x.data_ptr(), n_chunks, 150, wsb.data_ptr(), wsb.numel(), code, st) == 0
+        def timed(fn, n):
+            ts = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ts.append(1e3 * a.elapsed_time(b) / n)
+            return sorted(ts)[2]
+        layer(3); torch.cuda.synchronize()
+        out = {}
+        for which, nm in enumerate(("qkv", "attention", "post")):
+            def rep(w=which):
+                assert eng.lib.resep_layer_kernel_repeat(eng.handle, 0, 1, w, x.data_ptr(), n_chunks, 150, wsb.data_ptr(), wsb.numel(), code, 32, 0, st) == 0
+            rep(); torch.cuda.synchronize()
+            out[nm] = timed(rep, 32)
+            x.normal_()
+        out["layer_pdl"] = timed(lambda: layer(64), 64)
+        return out
+    lk = None
+    if args.precision in ("bf16", "fp16"):
+        try:
+            lk = layer_kernel_us()
+        except Exception as e:   # the measurement aid must never take the bench line down
+            lk = {"error": repr(e)}
     pk = peaks()
     reps = 5
     prof = sep.profile_kernels(lambda: [sep.separate_batch(mix) for _ in range(reps)])
@@ -438,7 +479,15 @@ def main():
     if top[0]:
         name, rec = top
         bound, work = kernel_work(name, BATCH, T)
-        avg_ms = rec["ms"] / rec["launches"]
+        avg_ms = rec["ms"] / rec["launches"]       # one event pair per launch: includes event records, launch gaps, lost PDL overlap
+        pair_ms = avg_ms
+        method = "one CUDA-event pair around every launch of the kernel inside whole forwards"
+        if lk and "error" not in lk:
+            key = ("post" if name.startswith("k_post2_tc") else "qkv" if name.startswith("k_qkv2_tc")
+                   else "attention" if name.startswith(("k_attention_bf16_tma", "k_attn_tc")) else None)
+            if key and not name.endswith("(small)"):
+                avg_ms = lk[key] / 1e3
+                method = "32 serialised launches of the kernel (no PDL) between one CUDA-event pair, median of 5 (resep_layer_kernel_repeat)"
         frac_sust = None
         if bound == "tensor":
             # the profiling pass times each kernel alone at full clocks: the BURST cuBLAS figure is the honest denominator
@@ -462,7 +511,9 @@ def main():
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": pk["_src"] + (" (burst bf16: the kernel is timed alone in the profiling pass)" if bound == "tensor" else ""),
                     "frac_of_sustained_peak": frac_sust,
-                    "avg_launch_us": 1e3 * avg_ms, "launches_per_step": rec["launches"] / reps,
+                    "avg_launch_us": 1e3 * avg_ms, "avg_launch_method": method, "event_pair_per_launch_us": 1e3 * pair_ms,
+                    "layer_kernels_back_to_back_us": lk,
+                    "launches_per_step": rec["launches"] / reps,
                     "share_of_step": rec["ms"] / sum(r["ms"] for r in prof.values()),
                     "kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
         # all tensor-core work of the intra blocks together: (QKV + attention + out-proj + FFN FLOPs) / their summed time
@@ -475,6 +526,8 @@ def main():
                 w = 16 * shapes(BATCH, T)[3] * 98_304      # (kernel_work reports this HBM-bound kernel in bytes)
             tc_flops += w * reps
             tc_ms += v["ms"]
+        if lk and "error" not in lk and tc_ms > 0:      # the layer as the product runs it: 3 PDL launches, 64 layers back to back
+            tc_ms = lk["layer_pdl"] / 1e3 * reps * 16
         if tc_ms > 0:
             ach = tc_flops / (tc_ms / 1e3) / 1e12
             tensor_pipe = {"kernels": "k_qkv2_tc + intra attention + k_post2_tc (the 16 intra layers)", "achieved_tflops": ach,

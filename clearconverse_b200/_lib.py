@@ -75,6 +75,8 @@ SYMBOLS = {
     "resep_encoder_fwd": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "resep_layer_fwd": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p]),
+    "resep_layer_kernel_repeat": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "resep_linear_fwd": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]),
 }

@@ -1081,6 +1081,23 @@ int tc_linear_test(ResepHandle* h, const float* A, const float* W, const float* 
 // One transformer layer with tensor-core GEMMs.
 //   bf16 mode: y / qkv / ctx / hid are bf16 (half the bytes of the fp32 scratch regions they live in)
 //   tf32 mode: fp32 buffers holding tf32-rounded values; attention uses the fp32 kernel
+bool g_serial_launches = false;
+
+// Profiling aid behind resep_layer_kernel_repeat: ONE of the layer's three fused 16-bit kernels, `reps` times back to
+// back on the buffers a previous tc_run_layer call left behind.
+int tc_repeat_layer_kernel(ResepHandle* h, const LayerDev& lw, int which, float* o, int64_t rows, int n_seq, int seq_len,
+                           float* qkv, float* ctx, int reps, bool pdl, cudaStream_t st, bool intra) {
+  bf16 *qb = reinterpret_cast<bf16*>(qkv), *cb = reinterpret_cast<bf16*>(ctx);
+  g_serial_launches = !pdl;
+  int rc = RESEP_OK;
+  for (int i = 0; i < reps && rc == RESEP_OK; ++i)
+    rc = which == 0 ? launch_qkv2_tc(h, lw, o, qb, rows, st)
+       : which == 1 ? launch_attention_bf16(h, qb, cb, n_seq, seq_len, nullptr, nullptr, nullptr, 0, seq_len, st, intra)
+                    : launch_post2_tc(h, lw, cb, o, rows, st);
+  g_serial_launches = false;
+  return rc;
+}
+
 int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
                  const int* tile_seq, const int* tile_q0, int n_tiles, int max_seq_len, float* y, float* qkv, float* ctx, float* hid,
                  int precision, cudaStream_t st, bool intra) {

@@ -869,6 +869,26 @@ int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, i
   return run_layer(h, h->w.blk[blk].layers[layer], x, sd, ws, precision, static_cast<cudaStream_t>(stream));
 }
 
+int resep_layer_kernel_repeat(ResepHandle* h, int block, int layer, int which, float* x, int n_seq, int seq_len,
+                              void* workspace, size_t workspace_bytes, int precision, int reps, int pdl, void* stream) {
+  if (!h) return RESEP_EINVAL;
+  if (!x || block < 0 || block > 2 || layer < 0 || layer >= NL || n_seq <= 0 || seq_len <= 0 || which < 0 || which > 2 || reps <= 0)
+    return set_err(h, RESEP_EINVAL, "bad argument");
+  if (precision != RESEP_PREC_BF16 && precision != RESEP_PREC_FP16)
+    return set_err(h, RESEP_EINVAL, "resep_layer_kernel_repeat: the fused layer kernels exist in the bf16 and fp16 modes");
+  h->fmt16 = precision == RESEP_PREC_FP16;
+  h->w16_mode = h->fmt16 ? h->w16_mode_fp16 : h->w16_mode_bf16;
+  RESEP_CUDA(h, cudaSetDevice(h->device));
+  const int64_t rows = (int64_t)n_seq * seq_len;
+  Workspace ws = carve(workspace, rows, 0);
+  if (!workspace || workspace_bytes < ws.bytes)
+    return set_err(h, RESEP_EWORKSPACE, "workspace too small: need " + std::to_string(ws.bytes) + " bytes");
+  int rc;
+  if ((rc = tc_init(h))) return rc;
+  return tc_repeat_layer_kernel(h, h->w.blk[block].layers[layer], which, x, rows, n_seq, seq_len, ws.qkv, ws.ctx, reps, pdl != 0,
+                                static_cast<cudaStream_t>(stream), block < 2 && seq_len == CHUNK);
+}
+
 int resep_linear_fwd(ResepHandle* h, const float* A, const float* W, const float* bias, float* out, int64_t M, int N,
                      int K, int relu, int precision, void* stream) {
   if (!h) return RESEP_EINVAL;

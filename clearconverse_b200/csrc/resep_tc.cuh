@@ -6,6 +6,8 @@ namespace resep {
 
 // One TransformerEncoderLayer on o [rows,128] (fp32 residual stream, updated in place) with the
 // GEMMs and attention on tensor cores.  y/qkv/ctx/hid are scratch regions of the workspace.
+int tc_repeat_layer_kernel(ResepHandle* h, const LayerDev& lw, int which, float* o, int64_t rows, int n_seq, int seq_len,
+                           float* qkv, float* ctx, int reps, bool pdl, cudaStream_t st, bool intra);
 int tc_run_layer(ResepHandle* h, const LayerDev& lw, float* o, int64_t rows, int n_seq, int seq_len, const int* seq_off,
                  const int* tile_seq, const int* tile_q0, int n_tiles, int max_seq_len, float* y, float* qkv, float* ctx, float* hid,
                  int precision, cudaStream_t st, bool intra = false);

@@ -47,6 +47,7 @@ static int make_tmap_head(ResepHandle* h, CUtensorMap* m, const bf16* base, int6
 
 // Launch with programmatic dependent launch: the kernel may start while its predecessor in the stream drains; it
 // calls ptx::pdl_wait() before touching anything the predecessor produced.  RESEP_PDL=0 launches it serialised.
+extern bool g_serial_launches;   // profiling aid (resep_layer_kernel_repeat): launch without the PDL attribute
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   static const bool pdl = !(getenv("RESEP_PDL") && getenv("RESEP_PDL")[0] == '0');
@@ -54,7 +55,7 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  attr.val.programmaticStreamSerializationAllowed = pdl && !g_serial_launches ? 1 : 0;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }

@@ -211,6 +211,15 @@ int resep_encoder_fwd(ResepHandle* h, const float* mix, int64_t T, float* tokens
 int resep_layer_fwd(ResepHandle* h, int block, int layer, float* x, int n_seq, int seq_len,
                     void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* Measurement aid: launches ONE of the three fused kernels of that layer (bf16 / fp16 modes) `reps` times back to
+ * back on the buffers a preceding resep_layer_fwd call with the same arguments left in `workspace`, so that a pair of
+ * events around the call times the kernel itself, without per-launch event records or host gaps.
+ * which: 0 = LayerNorm + in-projection (k_qkv2_tc), 1 = attention, 2 = out-proj + LayerNorm + FFN (k_post2_tc).
+ * pdl: 0 = every launch waits for its predecessor to drain (a launch's duration includes its own set-up and tail),
+ * 1 = programmatic dependent launch as in the product path.  x is overwritten; the values are not meaningful. */
+int resep_layer_kernel_repeat(ResepHandle* h, int block, int layer, int which, float* x, int n_seq, int seq_len,
+                              void* workspace, size_t workspace_bytes, int precision, int reps, int pdl, void* stream);
+
 /* out[M,N] = A[M,K] . W[N,K]^T + bias, through the GEMM kernel of the given precision
  * (W, bias: DEVICE fp32).  For testing the tcgen05 path against the fp32 path. */
 int resep_linear_fwd(ResepHandle* h, const float* A, const float* W, const float* bias, float* out,
