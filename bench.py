@@ -202,6 +202,32 @@ def time_oracle(sds, items: int, reps: int, warmup: int = 1):
     return items * SECONDS / statistics.median(times), times, torch.get_num_threads()
 
 
+def time_oracle_other_configs(sds):
+    """CPU figures for BASELINE.md section 5 (opt-in, --cpu-other-configs): config 1 (1 x 4 s), config 3 (1 x 60 s) and a
+    bounded sample of config 4 as the product runs it (one B = 1 call per overlap segment, api.py:1073-1077)."""
+    import torch
+    from clearconverse_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = make_oracle(sds)
+    out = {"cores": torch.get_num_threads()}
+    def med(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return statistics.median(ts)
+    x1 = synth.synth_batch(1, 4 * SAMPLE_RATE, seed=1)
+    out["config1_1x4s_audio_s_per_s"] = 4.0 / med(lambda: m.separate_batch(x1), 5)
+    x3 = synth.synth_batch(1, 60 * SAMPLE_RATE, seed=3)
+    out["config3_1x60s_audio_s_per_s"] = 60.0 / med(lambda: m.separate_batch(x3), 3)
+    lens = synth.meeting_overlap_segments(720.0, seed=4)[:12]
+    segs = [synth.synth_mixture(n, 5000 + i)[0].unsqueeze(0) for i, n in enumerate(lens)]
+    t = med(lambda: [m.separate_batch(sg) for sg in segs], 1)
+    out["config4_b1_loop_audio_s_per_s"] = sum(lens) / SAMPLE_RATE / t
+    out["config4_sample"] = f"the first {len(lens)} of the meeting's segments ({sum(lens) / SAMPLE_RATE:.0f} s of audio), one B=1 call each"
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path.  speechbrain cannot be
     installed here, so this is the oracle port on the host cores; rank 0 alone runs it."""
@@ -243,6 +269,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-other-configs", action="store_true",
+                    help="also time the oracle on configs 1, 3 and a sample of config 4 (adds about a minute of CPU work)")
     ap.add_argument("--no-side-blocks", action="store_true",
                     help="skip the sustained / meeting / long_split / latency / cpu_baseline blocks (the ncu passes under "
                          "profiles/ use this: the timed step and its kernels are the same, the run is ~100x shorter)")
@@ -542,6 +570,8 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"the whole step (B={BATCH} x {SECONDS} s, coupled), oracle fp32 eager PyTorch, 1 warm-up + median of 5 "
                          f"({sum(times):.1f} s of CPU work)", "host_cpus": os.cpu_count()}
+        if args.cpu_other_configs:
+            cpu["other_configs"] = time_oracle_other_configs(sds)
 
     flops_step = None
     from clearconverse_b200.sharding import flops_of

@@ -46,6 +46,11 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "oracle/" not in src or f.endswith((".cu", ".cuh")), f
+    # development probes and microbenchmarks do not execute the oracle either (the accuracy tools live under tests/tools/)
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "scripts", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
 
 
 def test_weight_packing_roundtrip(sds):

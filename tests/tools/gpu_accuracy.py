@@ -3,7 +3,7 @@
 against the mixture with the SI-SNR delta next to it -- the delta is only meaningful where the reference SI-SNR is
 well-conditioned (tests/test_gpu_parity.py::si_snr_delta)."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from clearconverse_b200 import SepformerSeparation

@@ -1,7 +1,7 @@
 """Development probe: accuracy (max-abs vs the oracle, est-vs-est SI-SNR) and speed of the fp16 mode (full hi + lo
 weights, and RESEP_W16F=mixed) next to tf32 and bf16, over several weight seeds and shapes."""
 import json, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 if len(sys.argv) > 1 and sys.argv[1] == "worker":
     import torch

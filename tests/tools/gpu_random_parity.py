@@ -1,6 +1,6 @@
 """One-off robustness sweep: random ragged batches in every precision mode against per-item oracle calls."""
 import os, sys, random
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from clearconverse_b200 import SepformerSeparation

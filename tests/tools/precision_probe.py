@@ -5,7 +5,7 @@ Rounds GEMM operands the way the CUDA path does (activations to a 16-bit format,
 max-abs and the SI-SNR delta of tests/test_gpu_parity.py against the fp32 oracle.
 """
 import os, sys, itertools
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from oracle import functional_restatement as fr
