@@ -59,7 +59,7 @@ constexpr int OFF_PAR = OFF_W + NW * UNIT;
 constexpr int PAR_FLOATS = 2 * D + FFN;  // bo, b2, b1g (b1 with norm2's shift folded in)
 constexpr int OFF_RED = OFF_PAR + PAR_FLOATS * 4;   // [2][4][128] floats: LayerNorm partial sums / squares of the column quarters
 constexpr int OFF_BAR = OFF_RED + 8 * 128 * 4;
-constexpr int NBAR = 2 * NW + 15;
+constexpr int NBAR = 2 * NW + 16;
 constexpr int SMEM = OFF_BAR + NBAR * 8 + 16;
 // TMEM: three [128 x 128] fp32 regions whose roles rotate every tile (role 0 = Y: o' -> FFN2 accumulator; roles 1, 2 =
 // FFN1 chunk accumulators of the even / odd chunks, re-packed in place to bf16), region of (tile t, role) =
@@ -70,9 +70,8 @@ static_assert(SMEM <= 227 * 1024, "shared memory budget");
 }  // namespace post2
 
 struct Post2Args {
-  // by value: kernel parameters live in the constant bank, so the epilogues read them without touching the
-  // shared-memory port (which the MMA B operands and the weight TMA already keep ~80% busy)
-  float bo[D], b2[D], b1[FFN];   // b1 = b1g: FFN1 bias with norm2's shift folded in
+  const float* par;   // DEVICE: bo[128] | b2[128] | b1g[1024] (FFN1 bias with norm2's shift folded in), one bulk copy at kernel entry
+                      // (staging them from kernel parameters cost 3.8k cycles of register-indexed constant loads per launch)
   int64_t M;
   int dbg;            // development aid (RESEP_DBG): bit 0 = no weight TMA / no w_full waits
   long long* trace;   // development aid (RESEP_TRACE): [3 roles][256] (tag, clock) pairs of CTA 0; null in production
@@ -135,6 +134,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   uint64_t* yp_full = ctx_full + 11;       // leader: o'(t) stored in the tile's Y region by both CTAs (32 warp arrivals)
   uint64_t* yreg_free = ctx_full + 12;     // leader: both CTAs have the tile's result in registers (16 warp arrivals)
   uint64_t* stg_free = ctx_full + 13;      // local: the tile's result has left the staging area (which includes the ctx buffer)
+  uint64_t* par_full = ctx_full + 15;      // local: the parameter block has landed
   uint64_t* f26_done = ctx_full + 14;      // both: F2(t, 6) retired: its FFN1 slot is the Y region of tile t + 1 and may take o'(t + 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
@@ -151,8 +151,9 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   const int n_iters = pair < m_ptiles ? (m_ptiles - pair + npairs - 1) / npairs : 0;
   auto row0_of = [&](int it) { return ((pair + it * npairs) * 2 + (int)rank) * 128; };
 
-  for (int i = threadIdx.x; i < D; i += THREADS) { s_bo[i] = args.bo[i]; s_b2[i] = args.b2[i]; }
-  for (int i = threadIdx.x; i < FFN; i += THREADS) s_b1[i] = args.b1[i];
+#ifdef RESEP_TRACE_BUILD
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) args.trace[1531] = clock64();
+#endif
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmCtx); prefetch_tmap(&tmO); prefetch_tmap(&tmWo); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
     if (SPLIT) prefetch_tmap(&tmWoL);
@@ -161,10 +162,21 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
     mbar_init(ctx_full, 1); mbar_init(ctx_empty, 1); mbar_init(res_full, 1); mbar_init(res_empty, A_WARPS);
     mbar_init(out_full, 1); mbar_init(y_full, 2 * A_WARPS);
     for (int i = 0; i < 2; ++i) { mbar_init(&acch_full[i], 1); mbar_init(&hs_full[i], 2 * A_WARPS); }
-    mbar_init(accy_done, 1); mbar_init(yp_full, 2 * A_WARPS); mbar_init(yreg_free, 2 * B_WARPS); mbar_init(stg_free, 1); mbar_init(f26_done, 1);
+    mbar_init(accy_done, 1); mbar_init(yp_full, 2 * A_WARPS); mbar_init(yreg_free, 2 * B_WARPS); mbar_init(stg_free, 2); mbar_init(f26_done, 1);
+    mbar_init(par_full, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(par_full, PAR_FLOATS * 4);       // weights, not the previous kernel's output: no PDL wait needed
+    bulk_load_1d(par, args.par, PAR_FLOATS * 4, par_full);
+#ifdef RESEP_TRACE_BUILD
+    if (args.trace != nullptr && blockIdx.x == 0) args.trace[1530] = clock64();
+#endif
   }
-  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  if (warp == 1) {
+    tmem_alloc_pair<512>(tmem_slot);
+#ifdef RESEP_TRACE_BUILD
+    if (args.trace != nullptr && blockIdx.x == 0 && lane == 0) args.trace[1529] = clock64();
+#endif
+  }
   tc_fence_before();
   cluster_sync_all();                      // barriers of both CTAs are initialised before any remote arrive / TMA
   tc_fence_after();
@@ -355,6 +367,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
     const uint32_t yfull = mapa_u32(smem_u32(y_full), 0);
     const uint32_t ypfull = mapa_u32(smem_u32(yp_full), 0);
     const bool tracer = warp == 4 && lane == 0;
+    mbar_wait(par_full, 0);
     auto abar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(A_THREADS) : "memory"); };
     auto E1 = [&](int t, float2 (&v)[16]) {
       if (tracer) TR(1, 1000 + t);
@@ -482,17 +495,19 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t yregfree = mapa_u32(smem_u32(yreg_free), 0);
-    const bool elected = warp == 4 + A_WARPS && lane == 0;
-    auto bbar = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(B_THREADS) : "memory"); };
+    const bool elected = ((warp - 4 - A_WARPS) & 3) == 0 && lane == 0;   // one per column half: stores that half's two slabs
+    const bool tracer_b = warp == 4 + A_WARPS && lane == 0;
+    auto hbar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + hf), "n"(B_THREADS / 2) : "memory"); };
+    mbar_wait(par_full, 0);
     auto slab = [&](int g) -> uint8_t* { return smem + (g < 2 ? OFF_CTX + g * ATOM : OFF_STG + (g - 2) * ATOM); };
 #pragma unroll 1
     for (int t = 0; t < n_iters; ++t) {
       const uint32_t ycol = lane_base + 128u * (uint32_t)(t % 3) + 64 * hf;
       const int row0 = row0_of(t);
-      if (elected) TR(2, 2000 + t);
+      if (tracer_b) TR(2, 2000 + t);
       mbar_wait(accy_done, t & 1);             // every MMA up to F2(t, 7) has retired: Y(t) is final, ctx(t + 1) has been read
       tc_fence_after();
-      if (elected) TR(2, 2100 + t);
+      if (tracer_b) TR(2, 2100 + t);
       float2 v[32];
       tmem_ld32(ycol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(ycol + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[16]));
@@ -500,8 +515,10 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(yregfree);   // the region may become the odd FFN1 slot of tile t + 1
-      if (elected) TR(2, 2150 + t);
-      // the previous tile's TMA store has read the staging area (elected waited, everyone passed the barrier at the loop's end)
+      if (tracer_b) TR(2, 2150 + t);
+      // (the previous tile's TMA stores have read this half's slabs: its elected thread waited, everyone of the half passed
+      // the barrier at the loop's end.)  Slab by slab, so that the first store runs under the second slab's staging; the
+      // two column halves stage and store independently.
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2) {
         uint8_t* srow = slab(2 * hf + g2) + r * 128;
@@ -512,20 +529,21 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
           const float2 x1 = fadd2(v[16 * g2 + 2 * j + 1], make_float2(b.z, b.w));
           *reinterpret_cast<float4*>(srow + ((j ^ (r & 7)) << 4)) = make_float4(x0.x, x0.y, x1.x, x1.y);
         }
+        fence_proxy_async();
+        hbar();
+        if (elected) tma_store_2d(&tmO, slab(2 * hf + g2), 32 * (2 * hf + g2), row0);   // rows >= M are clipped
+        if (tracer_b) TR(2, 2160 + 10 * g2 + t);
       }
-      fence_proxy_async();
-      bbar();
       if (elected) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tma_store_2d(&tmO, slab(g), 32 * g, row0);   // rows >= M are clipped
         tma_store_commit();
-        tma_store_wait_read<0>();              // the staging area (and with it the ctx buffer) is free again
-        mbar_arrive(stg_free);
-        TR(2, 2200 + t);
+        tma_store_wait_read<0>();              // this half's slabs (for hf = 0: the ctx buffer) are free again
+        mbar_arrive(stg_free);                 // (two arrivals per tile)
+        if (tracer_b) TR(2, 2200 + t);
       }
-      bbar();                                  // nobody writes the next tile's result before the store has read this one
+      hbar();                                  // nobody writes the next tile's result before the store has read this one
     }
     if (elected) tma_store_wait<0>();
+    if (tracer_b) TR(2, 2300);
   }
   tc_fence_before();
 #ifdef RESEP_TRACE_BUILD
@@ -559,7 +577,7 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
   if (getenv("RESEP_TRACE") && !trace_buf) { cudaMalloc(&trace_buf, 1536 * 8); cudaMemset(trace_buf, 0, 1536 * 8); g_post_trace = trace_buf; }
   static const int dbg = getenv("RESEP_DBG") ? atoi(getenv("RESEP_DBG")) : 0;
   Post2Args a;
-  std::memcpy(a.bo, lw.h_post_par, D * 4); std::memcpy(a.b2, lw.h_post_par + 3 * D, D * 4); std::memcpy(a.b1, lw.h_b1g, FFN * 4);
+  a.par = lw.post_par;
   a.M = rows; a.dbg = dbg; a.trace = trace_buf;
   auto kern = f16 ? (split_ffn ? k_post2_tc<true, true, true> : split ? k_post2_tc<true, false, true> : k_post2_tc<false, false, true>)
                   : (split_ffn ? k_post2_tc<true, true, false> : split ? k_post2_tc<true, false, false> : k_post2_tc<false, false, false>);

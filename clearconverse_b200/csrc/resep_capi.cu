@@ -172,6 +172,9 @@ static int upload_weights(ResepHandle* h, const ResepWeights* w) {
           b1g[hh] = (float)acc;
         }
         t.h_b1g = b1g;
+        std::vector<float> pp(2 * D + FFN);
+        std::memcpy(pp.data(), s.out_proj_b, D * 4); std::memcpy(pp.data() + D, s.ffn2_b, D * 4); std::memcpy(pp.data() + 2 * D, b1g, FFN * 4);
+        F(t.post_par, pp.data(), pp.size());
         Bf(t.f1g_w_bf, t.f1g_w_bl, wg.data(), (size_t)FFN * D);
         Hf(t.f1g_w_h, wg.data(), (size_t)FFN * D);
       }

@@ -53,6 +53,7 @@ struct LayerDev {
   // bf16 hi / lo, fp16 hi / lo, and the HOST copy of b1g[1024]
   const bf16 *f1g_w_bf, *f1g_w_bl, *f1g_w_h[2];
   const float* h_b1g;
+  const float* post_par;    // DEVICE: out_b[128] | f2_b[128] | b1g[1024], one bulk copy into k_post2_tc's shared memory
 };
 struct BlockDev {
   LayerDev layers[NL];

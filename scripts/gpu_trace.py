@@ -20,6 +20,7 @@ lib = eng.lib
 lib.resep_debug_trace.argtypes = [C.POINTER(C.c_longlong)]
 print("rc", lib.resep_debug_trace(buf))
 t0 = min(buf[r * 512 + 1] for r in range(3) if buf[r * 512 + 1])
+print("setup: params staged", buf[1531] - t0, "barriers initialised", buf[1530] - t0, "tmem allocated", buf[1529] - t0)
 print("kernel entry", buf[1535] - t0, "setup done", buf[1534] - t0, "producer warp done", buf[1533] - t0, "exit", buf[1532] - t0)
 for r, name in enumerate(("MMA", "A", "B")):
     ev = [(buf[r * 512 + 2 * i], buf[r * 512 + 2 * i + 1] - t0) for i in range(256) if buf[r * 512 + 2 * i + 1]]
