@@ -10,7 +10,7 @@ from clearconverse_b200.metrics import si_snr_db
 torch.set_num_threads(os.cpu_count())
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 oracle = OracleSepformerSeparation(seed=0)
-seps = {p: SepformerSeparation(oracle.component_state_dicts(), device="cuda:0", precision=p, batch_mode="independent") for p in ("fp32", "tf32", "bf16")}
+seps = {p: SepformerSeparation(oracle.component_state_dicts(), device="cuda:0", precision=p, batch_mode="independent") for p in ("fp32", "tf32", "fp16", "bf16")}
 worst = {p: 0.0 for p in seps}
 for trial in range(6):
     lens = [rng.choice([16, 17, rng.randint(16, 3000), rng.randint(16, 20000), 1200 * rng.randint(1, 6) + rng.choice([0, 7, 8, 15])]) for _ in range(rng.randint(1, 6))]
@@ -24,5 +24,5 @@ for trial in range(6):
             worst[p] = max(worst[p], d)
             assert torch.isfinite(o).all(), (p, n)
     print(trial, lens, {p: f"{v:.2e}" for p, v in worst.items()}, flush=True)
-assert worst["fp32"] < 1e-4 and worst["tf32"] < 1e-3 and worst["bf16"] < 5e-2
+assert worst["fp32"] < 1e-4 and worst["tf32"] < 1e-3 and worst["fp16"] < 1e-3 and worst["bf16"] < 5e-2
 print("ok", worst)
