@@ -548,6 +548,24 @@ def main():
                     "launches_per_step": rec["launches"] / reps,
                     "share_of_step": rec["ms"] / sum(r["ms"] for r in prof.values()),
                     "kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        # the other two layer kernels against their own roofs (back-to-back durations, per launch)
+        if lk and "error" not in lk:
+            Mrows = shapes(BATCH, T)[3]
+            n_ch = shapes(BATCH, T)[2]
+            qkv_bytes, qkv_flops = Mrows * (512 + 768), Mrows * 98_304
+            att_flops = n_ch * 8 * 4 * 150 * 150 * 16
+            att_exp = n_ch * 8 * 150 * 150
+            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            sm_clock_hz = 1e6 * float(clocks.summary().get("sm_max_mhz") or 1965)     # (the kernels were timed at burst clocks)
+            roofline["other_layer_kernels"] = [
+                {"kernel": "k_qkv2_tc", "bound": "hbm", "us": lk["qkv"], "achieved": qkv_bytes / (lk["qkv"] * 1e-6) / 1e9, "unit": "GB/s",
+                 "peak": pk["hbm_gbs"], "frac": qkv_bytes / (lk["qkv"] * 1e-6) / 1e9 / pk["hbm_gbs"],
+                 "tensor_tflops": qkv_flops / (lk["qkv"] * 1e-6) / 1e12,
+                 "note": "algorithmic bytes: 512 B in + 768 B out per row; most of them are L2 hits inside the step"},
+                {"kernel": "intra attention", "bound": "instruction issue (HMMA + MUFU.EX2 per 16 x 16 block)", "us": lk["attention"],
+                 "tensor_tflops": att_flops / (lk["attention"] * 1e-6) / 1e12,
+                 "exp2_per_clk_per_sm": att_exp / (lk["attention"] * 1e-6) / (sm_clock_hz * n_sms),
+                 "note": "MUFU.EX2 peak 16 per clock per SM (scripts/microbench/attn_probe.cu)"}]
         # all tensor-core work of the intra blocks together: (QKV + attention + out-proj + FFN FLOPs) / their summed time
         tc_flops, tc_ms = 0.0, 0.0
         for k, v in prof.items():

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t sw128_f32_off(int row, int col) {   // fp32 
   return (uint32_t)((col >> 5) * post2::ATOM + row * 128 + ((((col & 31) >> 2) ^ (row & 7)) << 4));
 }
 
-template <bool SPLIT, bool SPLIT_FFN, bool F16>
+template <bool SPLIT, int FFN_SPLIT, bool F16>   // FFN_SPLIT: 0 = FFN weights single, 1 = both hi + lo, 2 = FFN2 only, 3 = FFN1 only
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(post2::THREADS, 1)
 k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CUtensorMap tmO,
            const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWoL,
@@ -111,7 +111,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
            const __grid_constant__ Post2Args args) {
   using namespace post2;
   constexpr int PARTS = SPLIT ? 2 : 1;          // out-proj weight operand: bf16 hi (+ lo)
-  constexpr int FPARTS = SPLIT_FFN ? 2 : 1;     // FFN weight operands
+  constexpr int F1PARTS = (FFN_SPLIT == 1 || FFN_SPLIT == 3) ? 2 : 1, F2PARTS = (FFN_SPLIT == 1 || FFN_SPLIT == 2) ? 2 : 1;   // FFN weight operands
   constexpr uint32_t IDESC = umma_idesc(F16 ? UMMA_F16 : UMMA_BF16, F16 ? UMMA_F16 : UMMA_BF16, 256, 128);
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -157,7 +157,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmCtx); prefetch_tmap(&tmO); prefetch_tmap(&tmWo); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
     if (SPLIT) prefetch_tmap(&tmWoL);
-    if (SPLIT_FFN) { prefetch_tmap(&tmW1L); prefetch_tmap(&tmW2L); }
+    if (F1PARTS == 2) prefetch_tmap(&tmW1L);
+    if (F2PARTS == 2) prefetch_tmap(&tmW2L);
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(ctx_full, 1); mbar_init(ctx_empty, 1); mbar_init(res_full, 1); mbar_init(res_empty, A_WARPS);
     mbar_init(out_full, 1); mbar_init(y_full, 2 * A_WARPS);
@@ -207,8 +208,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
         }
       };
       auto put_out = [&]() { put(&tmWo, &tmWoL, 0, (int)rank * 64, PARTS); };
-      auto put_f1 = [&](int c) { put(&tmW1, &tmW1L, 0, c * 128 + (int)rank * 64, FPARTS); };
-      auto put_f2 = [&](int c) { put(&tmW2, &tmW2L, c * 128, (int)rank * 64, FPARTS); };
+      auto put_f1 = [&](int c) { put(&tmW1, &tmW1L, 0, c * 128 + (int)rank * 64, F1PARTS); };
+      auto put_f2 = [&](int c) { put(&tmW2, &tmW2L, c * 128, (int)rank * 64, F2PARTS); };
       put_out();
       put_f1(0);
       put_f1(1);
@@ -286,7 +287,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
         const uint32_t d = region(t, 1 + (c & 1));
         const uint32_t a = tmem + TM_X;
 #pragma unroll
-        for (int part = 0; part < FPARTS; ++part) {
+        for (int part = 0; part < F1PARTS; ++part) {
           const uint32_t b = wait_unit();
           const uint64_t b0 = umma_desc_k_sw128(b), b1 = umma_desc_k_sw128(b + UNIT / 2);
           if (elect_one()) {
@@ -295,7 +296,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(d, a + 32 + 8 * k, b1 + 2 * k, IDESC, true);
             umma_commit_pair(&w_empty[st]);
-            if (part == FPARTS - 1) umma_commit_pair(&acch_full[c & 1]);
+            if (part == F1PARTS - 1) umma_commit_pair(&acch_full[c & 1]);
           }
           __syncwarp();
           advance();
@@ -309,7 +310,7 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
         if (c == 0) mbar_wait(yp_full, t & 1);           // o'(t) is in the Y region (stored after Y2, off E1's critical path)
         if (lane == 0) TR(0, 4000 + t * NCH + c);
 #pragma unroll
-        for (int part = 0; part < FPARTS; ++part) {
+        for (int part = 0; part < F2PARTS; ++part) {
           const uint32_t b = wait_unit();
           const uint64_t b0 = umma_desc_k_sw128(b), b1 = umma_desc_k_sw128(b + UNIT / 2);
           if (elect_one()) {
@@ -319,8 +320,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16_ts_pair(d, a + 64 + 32 * (k >> 1) + 8 * (k & 1), b1 + 2 * k, IDESC, true);
             umma_commit_pair(&w_empty[st]);
-            if (part == FPARTS - 1 && c == NCH - 2) umma_commit_pair(f26_done);
-            if (part == FPARTS - 1 && c == NCH - 1) umma_commit_pair(accy_done);
+            if (part == F2PARTS - 1 && c == NCH - 2) umma_commit_pair(f26_done);
+            if (part == F2PARTS - 1 && c == NCH - 1) umma_commit_pair(accy_done);
           }
           __syncwarp();
           advance();
@@ -561,7 +562,8 @@ k_post2_tc(const __grid_constant__ CUtensorMap tmCtx, const __grid_constant__ CU
 
 int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* o, int64_t rows, cudaStream_t st) {
   if (rows <= 0) return RESEP_OK;
-  const bool split = h->w16_mode >= 1, split_ffn = h->w16_mode == 1;
+  const bool split = h->w16_mode >= 1;
+  const int ffn_split = h->w16_mode == 1 ? 1 : h->w16_mode == 3 ? 2 : h->w16_mode == 4 ? 3 : 0;
   CUtensorMap tmCtx, tmO, tmWo, tmWoL, tmW1, tmW1L, tmW2, tmW2L;
   int rc;
   if ((rc = make_tmap<bf16>(h, &tmCtx, ctx, rows, D, 128))) return rc;
@@ -579,8 +581,12 @@ int launch_post2_tc(ResepHandle* h, const LayerDev& lw, const bf16* ctx, float* 
   Post2Args a;
   a.par = lw.post_par;
   a.M = rows; a.dbg = dbg; a.trace = trace_buf;
-  auto kern = f16 ? (split_ffn ? k_post2_tc<true, true, true> : split ? k_post2_tc<true, false, true> : k_post2_tc<false, false, true>)
-                  : (split_ffn ? k_post2_tc<true, true, false> : split ? k_post2_tc<true, false, false> : k_post2_tc<false, false, false>);
+  auto pick = [&](auto f16_c) {
+    constexpr bool F = decltype(f16_c)::value;
+    return !split ? k_post2_tc<false, 0, F> : ffn_split == 1 ? k_post2_tc<true, 1, F> : ffn_split == 2 ? k_post2_tc<true, 2, F>
+         : ffn_split == 3 ? k_post2_tc<true, 3, F> : k_post2_tc<true, 0, F>;
+  };
+  auto kern = f16 ? pick(std::true_type{}) : pick(std::false_type{});
   RESEP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, post2::SMEM));
   static int max_pairs = 0;                // CTA pairs the device can hold at once (one CTA per SM)
   if (max_pairs == 0) {

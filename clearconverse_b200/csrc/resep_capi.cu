@@ -653,7 +653,8 @@ int resep_create(const ResepConfig* cfg, const ResepWeights* w, int device, Rese
     else if (!strcmp(m, "mixed")) h->w16_mode = 2;    // default
   }
   h->w16_mode_bf16 = h->w16_mode;
-  if (const char* m = getenv("RESEP_W16F")) h->w16_mode_fp16 = !strcmp(m, "mixed") ? 2 : !strcmp(m, "single") ? 0 : 1;
+  if (const char* m = getenv("RESEP_W16F"))   // fp16 mode: which weights are hi + lo ("ffn2" / "ffn1": the attention projections and that FFN matrix)
+    h->w16_mode_fp16 = !strcmp(m, "mixed") ? 2 : !strcmp(m, "single") ? 0 : !strcmp(m, "ffn2") ? 3 : !strcmp(m, "ffn1") ? 4 : 1;
   if (const char* g = getenv("RESEP_GRAPH")) h->use_graphs = g[0] != '0';
   int rc = upload_weights(h, w);
   if (rc) {

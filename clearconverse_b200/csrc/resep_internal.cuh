@@ -121,7 +121,10 @@ struct ResepHandle {
   // what the 16-bit kernels of the CURRENT call compute in: 0 = bf16 (RESEP_PREC_BF16), 1 = fp16 (RESEP_PREC_FP16, every
   // weight hi + lo).  Set by the forward entry points from the precision argument.
   int fmt16 = 0;
-  int w16_mode_fp16 = 1;    // the fp16 mode's setting: every weight hi + lo (RESEP_W16F=mixed: FFN weights single fp16)
+  // the fp16 mode's setting.  Default 1: every weight as fp16 hi + lo.  Measured worst max-abs over four weight seeds x four
+  // shapes / config-2 throughput: this 7.3e-4 / 33.5 k; FFN1 single, the rest hi + lo (RESEP_W16F=ffn2) 7.5e-4 / 36.5 k -- but 1.09e-3
+  // at the full config-2 batch, outside the 1e-3 contract; FFN2 single (ffn1) 9.4e-4 / 36.2 k; both FFN single (mixed) 8.7e-4 / 39.9 k
+  int w16_mode_fp16 = 1;
   int w16_mode_bf16 = 2;    // the bf16 mode's weight-operand setting (RESEP_W16), restored when a bf16 call follows an fp16 one
   bool prof_on = false;   // resep_profile(): bracket every launch with CUDA events
   struct ProfRec { cudaEvent_t a, b; const char* name; };
