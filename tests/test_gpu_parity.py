@@ -707,6 +707,39 @@ def test_layer_entry_point_matches_oracle_layer(make_sep, oracle, prec, tol, blo
     assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_layer_kernel_repeat_is_the_layer_in_three_launches(make_sep, prec):
+    """``resep_layer_kernel_repeat`` (the measurement aid behind bench.py's roofline): launching the layer's three fused
+    kernels one after the other through it reproduces ``resep_layer_fwd`` bit for bit -- it times the product's kernels,
+    not stand-ins -- and it rejects what it cannot run."""
+    sep = make_sep(prec, "coupled")
+    eng = sep._engine
+    code = {"bf16": 2, "fp16": 3}[prec]
+    n_seq, seq_len = 7, 150
+    rows = n_seq * seq_len
+    x = torch.randn(rows, 128, generator=torch.Generator().manual_seed(5)).cuda()
+    lens = (C.c_int64 * 1)(16 + 8 * (rows + 300))
+    need = C.c_size_t()
+    assert eng.lib.resep_workspace_bytes(eng.handle, 1, lens, code, C.byref(need)) == 0
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a, b = x.clone(), x.clone()
+    assert eng.lib.resep_layer_fwd(eng.handle, 1, 2, a.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(), code, st) == 0
+    torch.cuda.synchronize()
+    for which in (0, 1, 2):
+        for pdl in (0, 1):
+            c = b.clone() if which == 2 else b         # (the third kernel updates x in place: run it on a copy until the last call)
+            rc = eng.lib.resep_layer_kernel_repeat(eng.handle, 1, 2, which, c.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(),
+                                                   code, 1, pdl, st)
+            assert rc == 0, eng.lib.resep_last_error(eng.handle)
+    torch.cuda.synchronize()
+    assert torch.equal(c, a)
+    assert eng.lib.resep_layer_kernel_repeat(eng.handle, 1, 2, 3, b.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(), code, 1, 0, st) != 0
+    assert eng.lib.resep_layer_kernel_repeat(eng.handle, 1, 2, 0, b.data_ptr(), n_seq, seq_len, ws.data_ptr(), ws.numel(), 0, 1, 0, st) != 0
+    assert eng.lib.resep_layer_kernel_repeat(eng.handle, 1, 2, 0, b.data_ptr(), n_seq, seq_len, ws.data_ptr(), 16, code, 1, 0, st) != 0
+    assert sep.separate_batch(synth_batch(1, 4000, 1)).shape == (1, 4000, 2)      # the handle stays usable
+
+
 def test_separator_releases_gpu_memory_when_dropped(sds, cuda_lib_built):
     """Upstream's object frees its memory when it goes out of scope; so must the drop-in (the engine
     registry used to hold a strong reference, leaking weights, workspaces, static I/O buffers and graphs)."""
