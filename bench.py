@@ -347,7 +347,7 @@ def main():
         out["layer_pdl"] = timed(lambda: layer(64), 64)
         return out
     lk = None
-    if args.precision in ("bf16", "fp16"):
+    if args.precision in ("bf16", "fp16") and not args.no_side_blocks:      # (--no-side-blocks: profiler passes want one plain forward)
         try:
             lk = layer_kernel_us()
         except Exception as e:   # the measurement aid must never take the bench line down
