@@ -42,6 +42,7 @@ UNIT = "audio-s/s"
 SAMPLE_RATE = 8000
 BATCH, SECONDS = 16, 4
 T = SECONDS * SAMPLE_RATE
+DEPTH = 4          # forwards in flight in the pipelined driver (separate_stream: one CUDA stream, workspace and graph set per lane)
 WORKLOAD = "resepformer-wsj02mix random-init, batch 16 x 4 s synthetic 8 kHz 2-speaker mixtures (BASELINE configs[1])"
 
 
@@ -371,13 +372,13 @@ def main():
     audio_s = world * BATCH * SECONDS * args.steps
     single_value = audio_s / (single_ms.item() / 1e3)
 
-    # ---------------- device-resident throughput (`value`): the same K forwards through the pipelined driver, two in
-    # flight on two CUDA streams (a forward's memory transformer is 24 latency-bound launches on 4-56 CTAs: the other
-    # forward's intra block fills the machine meanwhile).  Inputs are rotated over 64 device-resident batches
-    # (128 MiB > the 126 MB L2) instead of flushing L2, which would serialise the two lanes.
+    # ---------------- device-resident throughput (`value`): the same K forwards through the pipelined driver, four in
+    # flight on four CUDA streams (a forward's memory transformer is 24 latency-bound launches on 4-56 CTAs and every
+    # persistent layer kernel ends in a partly filled last round: the other forwards' kernels fill those SMs).  Inputs are rotated over 64 device-resident batches
+    # (128 MiB > the 126 MB L2) instead of flushing L2, which would serialise the lanes.
     NROT = 64
     dev_mixes = [torch.roll(mix, i, 0).contiguous() for i in range(NROT)]
-    for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(max(args.warmup, 4))), depth=2, device_out=True):
+    for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(max(args.warmup, 3 * DEPTH))), depth=DEPTH, device_out=True):   # every lane: eager, capture, first replay
         pass
     barrier()
     l0 = sep.launch_count()
@@ -386,7 +387,7 @@ def main():
         t_wall0 = time.perf_counter()
         ev0.record()
         n_done = 0
-        for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(args.steps)), depth=2, device_out=True):
+        for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(args.steps)), depth=DEPTH, device_out=True):
             n_done += 1                                    # (each result is synchronised before it is yielded)
         ev1.record()
         barrier()
@@ -403,14 +404,14 @@ def main():
     # step's input H2D and its result D2H inside the timed region; `separate_stream` (the batched driver) overlaps
     # the copies of neighbouring steps with the kernels.  The serial form (one blocking separate_batch + copy per
     # step, what a single api.py call does) is reported next to it.
-    host_outs = [torch.empty(BATCH, T, 2, dtype=torch.float32).pin_memory() for _ in range(3)]
+    host_outs = [torch.empty(BATCH, T, 2, dtype=torch.float32).pin_memory() for _ in range(DEPTH + 1)]
     host_ins = [host_mix, host_mix.clone().pin_memory()]
-    for _ in sep.separate_stream((host_ins[i & 1] for i in range(3)), host_outs, depth=2):
+    for _ in sep.separate_stream((host_ins[i & 1] for i in range(3 * DEPTH)), host_outs, depth=DEPTH):
         pass
     barrier()
     t0 = time.perf_counter()
     n_out = 0
-    for out in sep.separate_stream((host_ins[i & 1] for i in range(args.steps)), host_outs, depth=2):
+    for out in sep.separate_stream((host_ins[i & 1] for i in range(args.steps)), host_outs, depth=DEPTH):
         n_out += 1
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -461,7 +462,7 @@ def main():
     ev0s, ev1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks_s:
         ev0s.record()
-        for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(sust_steps)), depth=2, device_out=True):
+        for _ in sep.separate_stream((dev_mixes[i % NROT] for i in range(sust_steps)), depth=DEPTH, device_out=True):
             pass
         ev1s.record()
         barrier()
@@ -605,7 +606,7 @@ def main():
         "dtype": args.precision, "data": "synthetic",
         "config": bench_config(world),
         "notes": {"weights": "random-init (seed 0); bf16 operands (in-proj / out-proj / output_fc weights as bf16 hi+lo, FFN weights single bf16), fp32 accumulate",
-                  "driver": "two forwards in flight on two CUDA streams, each with its own 0.3 GB workspace "
+                  "driver": "four forwards in flight on four CUDA streams, each with its own 0.3 GB workspace "
                             "(single_forward: one at a time, 256 MiB L2 flush between steps)"},
         "single_forward": {"value": single_value, "ms_per_step": single_ms.item() / args.steps,
                            "note": "one forward at a time on one stream, per-step CUDA events, L2 flushed between steps"},
@@ -613,7 +614,7 @@ def main():
         "sustained": sustained,
         "copy_probe": copy_probe,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * T * 4, "d2h_bytes_per_step": BATCH * T * 2 * 4,
-                "api": "SepformerSeparation.separate_stream (pinned host batches in, pinned host results out, copies overlapped, two forwards in flight)",
+                "api": "SepformerSeparation.separate_stream (pinned host batches in, pinned host results out, copies overlapped, four forwards in flight)",
                 "serial_value": e2e_serial_value, "serial_api": "separate_batch(host) + blocking copy per step"},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -42,6 +42,8 @@ _NEXT_ID = [1]
 # issued on the caller's stream while a separate_stream generator is half consumed (or was abandoned) never touches
 # a buffer or workspace that a lane stream may still be using.
 SYNC_LANE = "sync"
+# compute lanes of separate_stream (CUDA streams with their own workspace and graph set); slot s of the pipeline runs on lane s % N_LANES
+N_LANES = max(1, min(4, int(os.environ.get("RESEP_LANES", "4"))))
 
 
 def _destroy_handle(lib, handle):
@@ -312,7 +314,7 @@ def _resep_separate_static(host_or_dev_mix: torch.Tensor, offs: list[int], lens:
     if eng is None:
         raise RuntimeError("clearconverse_b200: separator engine was destroyed")
     _, est_buf = eng.static_io(offs, lens, host_or_dev_mix.numel(), slot)
-    eng.forward(host_or_dev_mix, offs, lens, precision, batch_mode, out=est_buf, lane=slot & 1)
+    eng.forward(host_or_dev_mix, offs, lens, precision, batch_mode, out=est_buf, lane=slot % N_LANES)
     return est_buf
 
 
@@ -530,13 +532,15 @@ class SepformerSeparation:
         may also be a LIST of 1-D segments of different lengths (device or pinned host): it is separated with per-item
         semantics like ``separate_segments`` and yields a list of [T_i, n_spk] device tensors."""
         dev = self.device
-        # Two compute streams, batches alternating between them (each lane has its own workspace and CUDA graphs): a
-        # forward spends ~12 % of its time in the memory transformer, whose latency-bound launches use few CTAs;
-        # the neighbouring batch's intra block fills those SMs (scripts/gpu_timeline.py, scripts/gpu_dual_stream.py).
+        # min(depth, N_LANES) compute streams, batches dealt to them in turn (each lane has its own workspace and CUDA
+        # graphs): a forward spends ~12 % of its time in the memory transformer, whose latency-bound launches use few
+        # CTAs, and every persistent layer kernel ends in a partly filled last round; the neighbouring batches' kernels
+        # fill those SMs (scripts/gpu_timeline.py, scripts/gpu_dual_stream.py; config 2, scripts/gpu_lanes.py: 1 lane
+        # 40.4 k audio-s/s, 2 lanes 43.1-43.5 k, 3 lanes 43.7-44.1 k, 4 lanes 44.3 k).
         if getattr(self, "_pipe_streams", None) is None:   # created once: the caching allocator keeps per-stream pools,
-            self._pipe_streams = [torch.cuda.Stream(dev) for _ in range(4)]   # fresh streams mean fresh cudaMallocs
-        lanes = self._pipe_streams[:2] if depth >= 2 else [self._pipe_streams[0]]
-        h2d, d2h = self._pipe_streams[2], self._pipe_streams[3]
+            self._pipe_streams = [torch.cuda.Stream(dev) for _ in range(N_LANES + 2)]   # fresh streams mean fresh cudaMallocs
+        lanes = self._pipe_streams[:max(1, min(depth, N_LANES))]
+        h2d, d2h = self._pipe_streams[N_LANES], self._pipe_streams[N_LANES + 1]
         caller = torch.cuda.current_stream(dev)
         for st in self._pipe_streams:
             st.wait_stream(caller)
@@ -556,7 +560,7 @@ class SepformerSeparation:
         try:
             for i, mix in enumerate(batches):
                 slot = i % depth
-                compute = lanes[slot & 1] if len(lanes) > 1 else lanes[0]     # the lane (workspace) of a slot is slot & 1
+                compute = lanes[slot % N_LANES % len(lanes)]     # the lane (workspace) of a slot is slot % N_LANES
                 if isinstance(mix, (list, tuple)):
                     # a ragged batch of 1-D segments (per-item semantics, as separate_segments): results stay on the device
                     segs = [s_.reshape(-1) for s_ in mix]
