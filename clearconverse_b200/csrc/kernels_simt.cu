@@ -35,7 +35,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // of _padfeature) are written as zeros.  With `o` != null the first transformer block's prologue is fused in:
 // o = x0 + pe[frame in chunk] (hc is zero for the first block, so its skip input is x0 itself): the separate
 // k_block_prologue pass over the same 33 MB (config 2) disappears.
-constexpr int ENC_ROWS = 30;
+constexpr int ENC_ROWS = 50;            // rows per CTA (A/B on config 2: 30 rows 37.3 us, 50 rows 33.0 us, 75 rows 37.5 us per launch)
 __global__ void __launch_bounds__(D) k_encoder_chunked(const float* __restrict__ mix, const float* __restrict__ enc_w,
                                                        const int64_t* __restrict__ item_off,
                                                        const int64_t* __restrict__ item_len,
