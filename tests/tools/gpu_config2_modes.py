@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
-from clearconverse_b200 import SepformerSeparation, weights
+from clearconverse_b200 import SepformerSeparation
 from clearconverse_b200.synth import synth_batch
 from oracle.resepformer_oracle import OracleSepformerSeparation
 torch.set_num_threads(os.cpu_count())
